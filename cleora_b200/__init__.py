@@ -1,0 +1,117 @@
+"""cleora_b200 -- B200-native drop-in for pycleora's iterated Markov-propagation embedding loop.
+
+Host-side mirror of the reference's public hot-path API (``pycleora/__init__.py``): ``SparseMatrix``,
+``embed()``, ``whiten_embeddings()``, ``embed_using_baseline_cleora()`` with identical signatures and error
+behaviour.  Every numerical step runs in hand-written sm_100a CUDA kernels behind the C ABI in
+``include/cleora_b200.h``; nothing here falls back to numpy for compute (the only numpy call on the path is the
+``d x d`` ``numpy.linalg.eigh`` that the reference itself makes, served to the library through a callback).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+from .pycleora import SparseMatrix
+
+__all__ = ["SparseMatrix", "embed", "whiten_embeddings", "embed_using_baseline_cleora",
+           "DEFAULT_FEATURE_DIM", "DEFAULT_NUM_ITERATIONS"]
+
+DEFAULT_FEATURE_DIM = 256          # pycleora/__init__.py:12
+DEFAULT_NUM_ITERATIONS = 40        # pycleora/__init__.py:13
+
+_DEVICE_NORMS = {"l2": _lib.NORM_L2_NUMPY, "l1": _lib.NORM_L1_NUMPY, "none": _lib.NORM_NONE}
+
+
+def _validate_propagation(propagation: str) -> None:
+    if propagation not in ("left", "symmetric"):   # pycleora/__init__.py:24-26
+        raise ValueError(f"Unknown propagation type: '{propagation}'. Use 'left' or 'symmetric'.")
+
+
+def whiten_embeddings(embeddings: np.ndarray, n_components: Optional[int] = None) -> np.ndarray:
+    """PCA whitening, ``pycleora/__init__.py:130-164``: f64 mean and covariance (K2), ``eigh``, f32 transform (K3)."""
+    x = np.ascontiguousarray(embeddings, dtype=np.float32)
+    n, d = x.shape
+    if n <= 1:
+        return embeddings.copy()
+    dout = d if n_components is None else min(int(n_components), d)
+    out = np.empty((n, dout), np.float32)
+    check(_lib.lib().cleora_whiten_embeddings(ptr(x, _lib.c_f32p), n, d, dout, ptr(out, _lib.c_f32p)))
+    return out
+
+
+def embed_using_baseline_cleora(graph: SparseMatrix, feature_dim: int, iter: int) -> np.ndarray:  # noqa: A002
+    """pycleora/__init__.py:16-21."""
+    return embed(graph, feature_dim, iter, whiten=True)
+
+
+def embed(
+    graph: SparseMatrix,
+    feature_dim: int = DEFAULT_FEATURE_DIM,
+    num_iterations: Union[int, str] = DEFAULT_NUM_ITERATIONS,
+    propagation: str = "left",
+    normalization: str = "l2",
+    seed: int = 0,
+    initial_embeddings: Optional[np.ndarray] = None,
+    num_workers: Optional[int] = None,
+    callback: Optional[Callable[[int, np.ndarray], None]] = None,
+    residual_weight: float = 0.0,
+    convergence_threshold: float = 0.0,
+    whiten: bool = True,
+) -> np.ndarray:
+    """``pycleora.embed`` (pycleora/__init__.py:51-127) with the whole loop resident on the GPU.
+
+    Dispatch (results as the reference computes them):
+      * ``whiten=False``, l2, no callback / initial embeddings -> ``graph.embed_fast[_convergence]`` (Rust fast path);
+      * no callback -> one device-resident call for all iterations (``cleora_embed``);
+      * callback given -> the reference's per-iteration loop, each stage still on the device, with the host array
+        handed to the callback after every iteration.
+    """
+    if isinstance(num_iterations, str):
+        if num_iterations == "auto":
+            num_iterations = DEFAULT_NUM_ITERATIONS
+        else:
+            raise ValueError(f"num_iterations must be an int or 'auto', got '{num_iterations}'")
+    use_fast_path = initial_embeddings is None and callback is None and normalization == "l2" and not whiten
+    if use_fast_path:
+        if convergence_threshold > 0:
+            embeddings, _ = graph.embed_fast_convergence(
+                feature_dim, num_iterations, propagation=propagation, seed=seed, residual_weight=residual_weight,
+                convergence_threshold=convergence_threshold, num_workers=num_workers)
+            return embeddings
+        return graph.embed_fast(feature_dim, num_iterations, propagation=propagation, seed=seed,
+                                residual_weight=residual_weight, num_workers=num_workers)
+
+    _validate_propagation(propagation)
+    if normalization not in ("l2", "l1", "none", "spectral"):
+        raise ValueError(f"Unknown normalization method: {normalization}. Use 'l2', 'l1', 'spectral', or 'none'.")
+    if normalization == "spectral":
+        raise ValueError("normalization='spectral' is outside the accelerated path (an SVD per iteration); "
+                         "use 'l2', 'l1' or 'none'")
+    if initial_embeddings is not None:
+        x0 = initial_embeddings.astype(np.float32)
+        if x0.shape[0] != graph.num_entities:
+            raise ValueError(
+                f"initial_embeddings has {x0.shape[0]} rows but graph has {graph.num_entities} entities")
+    else:
+        x0 = None
+
+    if callback is None:
+        out, _ = graph.embed_device(feature_dim, num_iterations, propagation, _DEVICE_NORMS[normalization], seed, x0,
+                                    residual_weight, convergence_threshold, whiten)
+        return out
+
+    # per-iteration path: one device-resident iteration at a time so the callback sees every iterate
+    embeddings = x0 if x0 is not None else graph.initialize_deterministically(feature_dim, seed)
+    for i in range(num_iterations):
+        prev = embeddings
+        embeddings, _ = graph.embed_device(embeddings.shape[1], 1, propagation, _DEVICE_NORMS[normalization], seed,
+                                           embeddings, residual_weight, 0.0, whiten)
+        callback(i, embeddings)
+        if convergence_threshold > 0 and i > 0:
+            diff = embeddings.astype(np.float64, copy=False) - prev.astype(np.float64, copy=False)
+            if float(np.sqrt(np.mean(diff * diff))) < convergence_threshold:   # _compute_rmse, :974-976
+                break
+    return embeddings

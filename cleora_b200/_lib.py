@@ -1,0 +1,136 @@
+"""ctypes prototypes for libcleora_b200.so (include/cleora_b200.h).
+
+This module is the *only* place the shared library is loaded.  It fails loudly when the library has not been
+built -- there is no Python/numpy fallback for any compute entry point (the CPU oracle under ``oracle/`` is test
+infrastructure and is never imported from here).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcleora_b200.so")
+
+OK, ERR_VALUE, ERR_RUNTIME, ERR_CUDA = 0, 1, 2, 3
+MARKOV = {"left": 0, "symmetric": 1}
+NORM_NONE, NORM_L2_RUST, NORM_L2_NUMPY, NORM_L1_NUMPY = 0, 1, 2, 3
+
+c_i64p = C.POINTER(C.c_int64)
+c_u32p = C.POINTER(C.c_uint32)
+c_u64p = C.POINTER(C.c_uint64)
+c_u8p = C.POINTER(C.c_uint8)
+c_f32p = C.POINTER(C.c_float)
+c_f64p = C.POINTER(C.c_double)
+
+EIGH_FN = C.CFUNCTYPE(C.c_int, c_f64p, c_f64p, C.c_int64, C.c_void_p)
+
+# name -> (restype, argtypes); every symbol declared in include/cleora_b200.h
+PROTOTYPES = {
+    "cleora_last_error": (C.c_char_p, []),
+    "cleora_version": (C.c_char_p, []),
+    "cleora_device_count": (C.c_int, []),
+    "cleora_set_device": (C.c_int, [C.c_int]),
+    "cleora_graph_from_lines": (C.c_int, [C.c_char_p, c_i64p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "cleora_graph_from_files": (C.c_int, [C.POINTER(C.c_char_p), C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "cleora_graph_from_pairs": (C.c_int, [c_u32p, c_u32p, C.c_int64, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "cleora_graph_from_csr": (C.c_int, [c_i64p, c_u32p, c_f32p, c_f32p, c_f32p, c_u64p, C.c_int64, C.c_int64,
+                                        C.c_int64, C.POINTER(C.c_void_p)]),
+    "cleora_graph_destroy": (None, [C.c_void_p]),
+    "cleora_graph_release_device": (C.c_int, [C.c_void_p]),
+    "cleora_graph_num_entities": (C.c_int64, [C.c_void_p]),
+    "cleora_graph_num_cols": (C.c_int64, [C.c_void_p]),
+    "cleora_graph_num_edges": (C.c_int64, [C.c_void_p]),
+    "cleora_graph_copy_csr": (C.c_int, [C.c_void_p, c_i64p, c_u32p, c_f32p, c_f32p]),
+    "cleora_graph_copy_row_sums": (C.c_int, [C.c_void_p, c_f32p]),
+    "cleora_graph_copy_entity_hashes": (C.c_int, [C.c_void_p, c_u64p]),
+    "cleora_graph_copy_column_ids": (C.c_int, [C.c_void_p, c_u8p]),
+    "cleora_graph_entity_ids_nbytes": (C.c_int64, [C.c_void_p]),
+    "cleora_graph_copy_entity_ids": (C.c_int, [C.c_void_p, C.c_char_p, c_i64p]),
+    "cleora_graph_set_entity_ids": (C.c_int, [C.c_void_p, C.c_char_p, c_i64p, C.c_int64]),
+    "cleora_graph_set_descriptor": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p]),
+    "cleora_graph_set_column_ids": (C.c_int, [C.c_void_p, c_u8p, C.c_int64]),
+    "cleora_graph_col_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "cleora_graph_col_id": (C.c_int, [C.c_void_p, C.c_int]),
+    "cleora_graph_find_entity": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "cleora_hash_entity": (C.c_uint64, [C.c_char_p, C.c_int64]),
+    "cleora_initialize_deterministically": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_f32p]),
+    "cleora_markov_propagate": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int64, C.c_int, c_f32p]),
+    "cleora_l2_normalize": (C.c_int, [c_f32p, C.c_int64, C.c_int64, c_f32p]),
+    "cleora_embed_fast": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_float, c_f32p]),
+    "cleora_embed_fast_convergence": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_float,
+                                                C.c_float, c_f32p, c_i64p]),
+    "cleora_whiten_embeddings": (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int64, c_f32p]),
+    "cleora_embed": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_double,
+                               C.c_int, C.c_int, c_f32p, c_i64p, c_f64p]),
+    "cleora_set_eigh": (None, [EIGH_FN, C.c_void_p]),
+    "cleora_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cleora_host_free": (None, [C.c_void_p]),
+    "cleora_dev_graph_prepare": (C.c_int, [C.c_void_p]),
+    "cleora_dev_init": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cleora_dev_spmm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,
+                                  C.c_float, C.c_int, C.c_void_p]),
+    "cleora_dev_normalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "cleora_dev_col_sums": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
+    "cleora_dev_centered_gram": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cleora_dev_whiten_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_void_p]),
+    "cleora_dev_sq_diff_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "cleora_whiten_transform_from_cov": (C.c_int, [c_f64p, C.c_int64, C.c_int64, c_f32p]),
+    "cleora_dev_workspace_bytes": (C.c_int64, []),
+    "cleora_kernel_launch_count": (C.c_int64, []),
+}
+
+_lib = None
+_eigh_keepalive = None
+
+
+def _numpy_eigh(a_ptr, w_ptr, d, _user):
+    """numpy.linalg.eigh behind the C callback -- the very call the reference makes
+    (pycleora/__init__.py:145), so eigenvector signs/order follow the same LAPACK."""
+    try:
+        a = np.ctypeslib.as_array(a_ptr, shape=(d, d))
+        w = np.ctypeslib.as_array(w_ptr, shape=(d,))
+        vals, vecs = np.linalg.eigh(a)
+        a[:, :] = vecs
+        w[:] = vals
+        return 0
+    except Exception:  # noqa: BLE001 - must not propagate through the C frame
+        return 1
+
+
+def lib():
+    """Load libcleora_b200.so (once).  Raises ImportError with build instructions when it is missing."""
+    global _lib, _eigh_keepalive
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C cleora_b200/csrc`.  cleora_b200 has no CPU/numpy fallback.")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(L, name)       # AttributeError here means header and library are out of sync
+        fn.restype = res
+        fn.argtypes = args
+    if os.environ.get("CLEORA_B200_EIGH", "numpy") == "numpy":
+        _eigh_keepalive = EIGH_FN(_numpy_eigh)
+        L.cleora_set_eigh(_eigh_keepalive, None)
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    """Map a status code to the exception class the reference raises."""
+    if rc == OK:
+        return
+    msg = lib().cleora_last_error().decode("utf-8", "replace")
+    if rc == ERR_VALUE:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def ptr(a: np.ndarray, ctype):
+    return a.ctypes.data_as(ctype)

@@ -1,0 +1,651 @@
+// extern "C" surface of libcleora_b200 (see include/cleora_b200.h): handles, error mapping, host-buffer entry
+// points (one per reference pymethod) and the device-resident embed loops.
+#include "../../include/cleora_b200.h"
+#include "device.cuh"
+#include "graph.hpp"
+
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <vector>
+
+struct cleora_graph : cleora::Graph {};
+
+namespace cleora {
+
+// ------------------------------------------------------------------------------------------------ errors / scratch
+static thread_local std::string t_err;
+void set_error(const std::string &msg) { t_err = msg; }
+std::atomic<int64_t> g_launches{0};
+
+void *Scratch::get(size_t bytes) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (p && (dev != device || bytes > cap)) release();
+    if (!p) {
+        cap = std::max<size_t>(bytes, 256);
+        device = dev;
+        CUDA_TRY(cudaMalloc(&p, cap));
+    }
+    return p;
+}
+void Scratch::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+Workspace &workspace() {
+    static thread_local Workspace ws;
+    return ws;
+}
+
+namespace {
+
+template <class F>
+int guarded(F &&f) {
+    try {
+        f();
+        return CLEORA_OK;
+    } catch (const BuildError &e) {
+        set_error(e.msg);
+        return CLEORA_ERR_VALUE;
+    } catch (const CudaFail &e) {
+        set_error(e.msg);
+        return CLEORA_ERR_CUDA;
+    } catch (const std::bad_alloc &) {
+        set_error("out of host memory");
+        return CLEORA_ERR_RUNTIME;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return CLEORA_ERR_RUNTIME;
+    }
+}
+
+struct ValueError : BuildError {};
+[[noreturn]] void value_error(const std::string &m) { throw BuildError{m}; }
+
+void require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        throw CudaFail{"no CUDA device available: libcleora_b200 has no CPU fallback"};
+    }
+}
+
+// RAII device buffer
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    void alloc(size_t count) {
+        free();
+        n = count;
+        if (count) CUDA_TRY(cudaMalloc((void **)&p, count * sizeof(T)));
+    }
+    void free() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { free(); }
+};
+
+void free_device_graph(DeviceGraph *dg) {
+    if (!dg) return;
+    cudaFree(dg->rowptr); cudaFree(dg->col); cudaFree(dg->left); cudaFree(dg->sym); cudaFree(dg->hash);
+    cudaFree(dg->long_rows);
+    delete dg;
+}
+
+// Upload the CSR once per (graph, device).  Arrays get 16 trailing elements of padding so tile loads never
+// touch unmapped memory.
+DeviceGraph &device_graph(Graph &g) {
+    require_device();
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (g.dev && g.dev->device != dev) { free_device_graph(g.dev); g.dev = nullptr; }
+    if (g.dev) return *g.dev;
+    auto *dg = new DeviceGraph();
+    dg->device = dev;
+    dg->n_rows = g.n_rows; dg->n_cols = g.n_cols; dg->nnz = g.nnz(); dg->row_offset = g.row_offset;
+    try {
+        const size_t pad = 16, nnz = (size_t)g.nnz();
+        CUDA_TRY(cudaMalloc((void **)&dg->rowptr, (g.rowptr.size() + pad) * sizeof(int64_t)));
+        CUDA_TRY(cudaMemcpy(dg->rowptr, g.rowptr.data(), g.rowptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc((void **)&dg->col, (nnz + pad) * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemset(dg->col, 0, (nnz + pad) * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpy(dg->col, g.col.data(), nnz * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc((void **)&dg->left, (nnz + pad) * sizeof(float)));
+        CUDA_TRY(cudaMemset(dg->left, 0, (nnz + pad) * sizeof(float)));
+        CUDA_TRY(cudaMemcpy(dg->left, g.left.data(), nnz * sizeof(float), cudaMemcpyHostToDevice));
+        if (!g.sym.empty()) {
+            CUDA_TRY(cudaMalloc((void **)&dg->sym, (nnz + pad) * sizeof(float)));
+            CUDA_TRY(cudaMemset(dg->sym, 0, (nnz + pad) * sizeof(float)));
+            CUDA_TRY(cudaMemcpy(dg->sym, g.sym.data(), nnz * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        if (!g.hash.empty()) {
+            CUDA_TRY(cudaMalloc((void **)&dg->hash, g.hash.size() * sizeof(uint64_t)));
+            CUDA_TRY(cudaMemcpy(dg->hash, g.hash.data(), g.hash.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        }
+    } catch (...) {
+        free_device_graph(dg);
+        throw;
+    }
+    g.dev = dg;
+    return *dg;
+}
+
+const float *values_of(const DeviceGraph &dg, int markov) {
+    if (markov == CLEORA_MARKOV_LEFT) return dg.left;
+    if (markov == CLEORA_MARKOV_SYMMETRIC) {
+        if (!dg.sym) value_error("graph was created without symmetric Markov values");
+        return dg.sym;
+    }
+    value_error("Unknown propagation. Use 'left' or 'symmetric'.");
+}
+
+void check_norm(int norm) {
+    if (norm < CLEORA_NORM_NONE || norm > CLEORA_NORM_L1_NUMPY) value_error("unknown normalization code");
+}
+
+// ------------------------------------------------------------------------------------------------ eigh
+cleora_eigh_fn g_eigh = nullptr;
+void *g_eigh_user = nullptr;
+
+// Default eigensolver: cuSOLVER Dsyevd on the current device (a library call for the small d x d step; the
+// reference's own GPU path does the same through torch.linalg.eigh, pycleora/__init__.py:990).
+int eigh_cusolver(double *a, double *w, int64_t d, void *) {
+    static thread_local cusolverDnHandle_t h = nullptr;
+    if (!h && cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) return 1;
+    const int n = (int)d;
+    int lwork = 0, info = 0;
+    try {
+        DevBuf<double> dA((size_t)d * d), dW((size_t)d);
+        DevBuf<int> dInfo(1);
+        CUDA_TRY(cudaMemcpy(dA.p, a, sizeof(double) * d * d, cudaMemcpyHostToDevice));
+        if (cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dA.p, n, dW.p, &lwork) !=
+            CUSOLVER_STATUS_SUCCESS)
+            return 2;
+        DevBuf<double> work((size_t)std::max(lwork, 1));
+        if (cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dA.p, n, dW.p, work.p, lwork,
+                             dInfo.p) != CUSOLVER_STATUS_SUCCESS)
+            return 3;
+        CUDA_TRY(cudaMemcpy(&info, dInfo.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (info != 0) return 4;
+        std::vector<double> colmajor((size_t)d * d);
+        CUDA_TRY(cudaMemcpy(colmajor.data(), dA.p, sizeof(double) * d * d, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(w, dW.p, sizeof(double) * d, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < d; ++i)
+            for (int64_t k = 0; k < d; ++k) a[i * d + k] = colmajor[(size_t)(k * d + i)];   // eigvec k = column k
+    } catch (const CudaFail &) {
+        return 5;
+    }
+    return 0;
+}
+
+// pycleora/__init__.py:145-156: eigh -> descending order -> scale = 1/sqrt(max(lambda,1e-10)) -> (V*scale) as f32.
+void transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T) {
+    std::vector<double> a(cov, cov + d * d), w((size_t)d);
+    int rc = g_eigh ? g_eigh(a.data(), w.data(), d, g_eigh_user) : eigh_cusolver(a.data(), w.data(), d, nullptr);
+    if (rc != 0) throw std::runtime_error("eigh failed with code " + std::to_string(rc));
+    for (int64_t k = 0; k < dout; ++k) {
+        const int64_t src = d - 1 - k;                          // argsort(eigenvalues)[::-1] on ascending input
+        const double scale = 1.0 / std::sqrt(std::max(w[(size_t)src], 1e-10));
+        for (int64_t i = 0; i < d; ++i) T[i * dout + k] = (float)(a[(size_t)(i * d + src)] * scale);
+    }
+}
+
+// Whitening of a device-resident matrix: Y[n,d] -> Z[n,dout].  Scratch: sums/cov (f64), mean32, T on device.
+struct WhitenState {
+    DevBuf<double> sums, cov;
+    DevBuf<float> mean32, T;
+    std::vector<double> h_cov;
+    std::vector<float> h_T;
+    int64_t d = 0, dout = 0;
+    void ensure(int64_t d_, int64_t dout_) {
+        if (d == d_ && dout == dout_) return;
+        d = d_; dout = dout_;
+        sums.alloc((size_t)d); cov.alloc((size_t)d * d); mean32.alloc((size_t)d); T.alloc((size_t)d * dout);
+        h_cov.resize((size_t)d * d); h_T.resize((size_t)d * dout);
+    }
+};
+
+struct Phase {
+    // optional per-phase device timing (cudaEvent pairs), summed at the end
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[8];
+    cudaStream_t st = nullptr;
+    cudaEvent_t a = nullptr;
+    void begin() {
+        if (!on) return;
+        cudaEventCreate(&a);
+        cudaEventRecord(a, st);
+    }
+    void end(int which) {
+        if (!on) return;
+        cudaEvent_t b;
+        cudaEventCreate(&b);
+        cudaEventRecord(b, st);
+        ev[which].push_back({a, b});
+    }
+    void collect(double *out) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        for (int i = 0; i < 8; ++i)
+            for (auto &p : ev[i]) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, p.first, p.second);
+                out[i] += ms;
+                cudaEventDestroy(p.first);
+                cudaEventDestroy(p.second);
+            }
+    }
+};
+enum { PH_H2D = 0, PH_INIT, PH_SPMM, PH_STATS, PH_EIGH, PH_APPLY, PH_RMSE, PH_D2H };
+
+void whiten_device(const float *Y, int64_t n, int64_t d, int64_t dout, float *Z, WhitenState &ws, cudaStream_t st,
+                   Phase &ph) {
+    ws.ensure(d, dout);
+    ph.begin();
+    launch_col_sums(Y, n, d, ws.sums.p, false, st);
+    launch_scale_f64(ws.sums.p, d, 1.0 / (double)n, st);                 // mean (f64)
+    launch_centered_gram(Y, n, d, ws.sums.p, ws.cov.p, st);
+    launch_scale_f64(ws.cov.p, d * d, 1.0 / (double)(n - 1), st);        // cov *= 1/(n-1)
+    launch_f64_to_f32(ws.sums.p, ws.mean32.p, d, st);                    // mean.astype(float32)
+    CUDA_TRY(cudaMemcpyAsync(ws.h_cov.data(), ws.cov.p, sizeof(double) * d * d, cudaMemcpyDeviceToHost, st));
+    ph.end(PH_STATS);
+    ph.begin();
+    CUDA_TRY(cudaStreamSynchronize(st));
+    transform_from_cov(ws.h_cov.data(), d, dout, ws.h_T.data());
+    CUDA_TRY(cudaMemcpyAsync(ws.T.p, ws.h_T.data(), sizeof(float) * d * dout, cudaMemcpyHostToDevice, st));
+    ph.end(PH_EIGH);
+    ph.begin();
+    launch_whiten_apply(Y, n, d, ws.mean32.p, ws.T.p, dout, Z, st);
+    ph.end(PH_APPLY);
+}
+
+}  // namespace
+}  // namespace cleora
+
+using namespace cleora;
+
+// ================================================================================================ misc
+extern "C" const char *cleora_last_error(void) { return t_err.c_str(); }
+extern "C" const char *cleora_version(void) { return "cleora_b200 0.1 (sm_100a)"; }
+extern "C" int cleora_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int cleora_set_device(int device) {
+    return guarded([&] { require_device(); CUDA_TRY(cudaSetDevice(device)); });
+}
+extern "C" uint64_t cleora_hash_entity(const char *bytes, int64_t len) { return xxh64(bytes, (size_t)len, 0); }
+extern "C" void cleora_set_eigh(cleora_eigh_fn fn, void *user) { g_eigh = fn; g_eigh_user = user; }
+extern "C" int cleora_host_alloc(size_t nbytes, void **out) {
+    return guarded([&] { require_device(); CUDA_TRY(cudaMallocHost(out, nbytes ? nbytes : 1)); });
+}
+extern "C" void cleora_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" int64_t cleora_dev_workspace_bytes(void) { return (int64_t)workspace().bytes(); }
+extern "C" int64_t cleora_kernel_launch_count(void) { return g_launches.load(); }
+
+// ================================================================================================ graph
+extern "C" int cleora_graph_from_lines(const char *buf, const int64_t *offsets, int64_t n_lines, const char *columns,
+                                       int64_t trim_n, cleora_graph_t **out) {
+    return guarded([&] {
+        auto g = build_from_lines(buf, offsets, n_lines, columns, trim_n);
+        *out = static_cast<cleora_graph_t *>(g.release());
+    });
+}
+extern "C" int cleora_graph_from_files(const char *const *paths, int64_t n_paths, const char *columns, int64_t trim_n,
+                                       cleora_graph_t **out) {
+    return guarded([&] {
+        if (n_paths <= 0) value_error("At least one file path is required");
+        std::vector<std::string> ps;
+        for (int64_t i = 0; i < n_paths; ++i) {
+            std::string p = paths[i];
+            auto ends = [&](const char *suf) { size_t l = std::strlen(suf); return p.size() >= l && p.compare(p.size() - l, l, suf) == 0; };
+            if (!ends(".tsv") && !ends(".csv") && !ends(".txt"))
+                value_error("Unsupported file format: " + p + ". Supported: .tsv, .csv, .txt");
+            ps.push_back(p);
+        }
+        auto g = build_from_files(ps, columns, trim_n);
+        *out = static_cast<cleora_graph_t *>(g.release());
+    });
+}
+extern "C" int cleora_graph_from_pairs(const uint32_t *u, const uint32_t *v, int64_t n_pairs, const char *column_name,
+                                       cleora_graph_t **out) {
+    return guarded([&] {
+        auto g = build_from_pairs(u, v, n_pairs, column_name ? column_name : "node");
+        *out = static_cast<cleora_graph_t *>(g.release());
+    });
+}
+extern "C" int cleora_graph_from_csr(const int64_t *rowptr, const uint32_t *col, const float *val_left,
+                                     const float *val_sym, const float *row_sum, const uint64_t *entity_hash,
+                                     int64_t n_rows, int64_t n_cols, int64_t row_offset, cleora_graph_t **out) {
+    return guarded([&] {
+        if (n_rows < 0 || n_cols < 0 || !rowptr) value_error("bad CSR shape");
+        if (rowptr[0] != 0) value_error("rowptr[0] must be 0");
+        for (int64_t r = 0; r < n_rows; ++r)
+            if (rowptr[r + 1] < rowptr[r]) value_error("rowptr must be non-decreasing");
+        const int64_t nnz = rowptr[n_rows];
+        for (int64_t k = 0; k < nnz; ++k)
+            if ((int64_t)col[k] >= n_cols) value_error("column index out of range");
+        auto g = std::make_unique<Graph>();
+        g->n_rows = n_rows; g->n_cols = n_cols; g->row_offset = row_offset;
+        g->rowptr.assign(rowptr, rowptr + n_rows + 1);
+        g->col.assign(col, col + nnz);
+        g->left.assign(val_left, val_left + nnz);
+        if (val_sym) g->sym.assign(val_sym, val_sym + nnz);
+        if (row_sum) g->row_sum.assign(row_sum, row_sum + n_rows);
+        if (entity_hash) g->hash.assign(entity_hash, entity_hash + n_rows);
+        g->column_id.assign((size_t)n_rows, 0);
+        *out = static_cast<cleora_graph_t *>(g.release());
+    });
+}
+extern "C" void cleora_graph_destroy(cleora_graph_t *g) {
+    if (!g) return;
+    free_device_graph(g->dev);
+    delete static_cast<Graph *>(g);
+}
+extern "C" int cleora_graph_release_device(cleora_graph_t *g) {
+    return guarded([&] { free_device_graph(g->dev); g->dev = nullptr; });
+}
+extern "C" int64_t cleora_graph_num_entities(const cleora_graph_t *g) { return g->n_rows; }
+extern "C" int64_t cleora_graph_num_cols(const cleora_graph_t *g) { return g->n_cols; }
+extern "C" int64_t cleora_graph_num_edges(const cleora_graph_t *g) { return g->nnz(); }
+extern "C" int cleora_graph_copy_csr(const cleora_graph_t *g, int64_t *rowptr, uint32_t *col, float *left, float *sym) {
+    return guarded([&] {
+        if (rowptr) std::copy(g->rowptr.begin(), g->rowptr.end(), rowptr);
+        if (col) std::copy(g->col.begin(), g->col.end(), col);
+        if (left) std::copy(g->left.begin(), g->left.end(), left);
+        if (sym) {
+            if (g->sym.empty() && g->nnz()) value_error("graph has no symmetric values");
+            std::copy(g->sym.begin(), g->sym.end(), sym);
+        }
+    });
+}
+extern "C" int cleora_graph_copy_row_sums(const cleora_graph_t *g, float *out) {
+    return guarded([&] { std::copy(g->row_sum.begin(), g->row_sum.end(), out); });
+}
+extern "C" int cleora_graph_copy_entity_hashes(const cleora_graph_t *g, uint64_t *out) {
+    return guarded([&] { std::copy(g->hash.begin(), g->hash.end(), out); });
+}
+extern "C" int cleora_graph_copy_column_ids(const cleora_graph_t *g, uint8_t *out) {
+    return guarded([&] { std::copy(g->column_id.begin(), g->column_id.end(), out); });
+}
+extern "C" int64_t cleora_graph_entity_ids_nbytes(const cleora_graph_t *g) {
+    int64_t t = 0;
+    for (const auto &s : g->ids) t += (int64_t)s.size();
+    return t;
+}
+extern "C" int cleora_graph_copy_entity_ids(const cleora_graph_t *g, char *buf, int64_t *offsets) {
+    return guarded([&] {
+        int64_t pos = 0;
+        offsets[0] = 0;
+        for (size_t i = 0; i < g->ids.size(); ++i) {
+            std::memcpy(buf + pos, g->ids[i].data(), g->ids[i].size());
+            pos += (int64_t)g->ids[i].size();
+            offsets[i + 1] = pos;
+        }
+    });
+}
+extern "C" int cleora_graph_set_entity_ids(cleora_graph_t *g, const char *buf, const int64_t *offsets, int64_t n) {
+    return guarded([&] {
+        if (n != g->n_rows) value_error("entity_ids must keep its length (" + std::to_string(g->n_rows) + ")");
+        g->ids.resize((size_t)n);
+        g->hash.resize((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            g->ids[(size_t)i].assign(buf + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
+            g->hash[(size_t)i] = xxh64(buf + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), 0);
+        }
+        g->id_index.clear();
+        if (g->dev && g->dev->hash) {
+            CUDA_TRY(cudaSetDevice(g->dev->device));
+            CUDA_TRY(cudaMemcpy(g->dev->hash, g->hash.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice));
+        }
+    });
+}
+extern "C" int cleora_graph_set_descriptor(cleora_graph_t *g, int col_a_id, const char *col_a_name, int col_b_id,
+                                           const char *col_b_name) {
+    return guarded([&] {
+        g->desc.col_a_id = col_a_id; g->desc.col_b_id = col_b_id;
+        g->desc.col_a_name = col_a_name ? col_a_name : ""; g->desc.col_b_name = col_b_name ? col_b_name : "";
+    });
+}
+extern "C" int cleora_graph_set_column_ids(cleora_graph_t *g, const uint8_t *ids, int64_t n) {
+    return guarded([&] {
+        if (n != g->n_rows) value_error("column_ids must have one entry per entity");
+        g->column_id.assign(ids, ids + n);
+    });
+}
+extern "C" const char *cleora_graph_col_name(const cleora_graph_t *g, int which) {
+    return which ? g->desc.col_b_name.c_str() : g->desc.col_a_name.c_str();
+}
+extern "C" int cleora_graph_col_id(const cleora_graph_t *g, int which) { return which ? g->desc.col_b_id : g->desc.col_a_id; }
+extern "C" int64_t cleora_graph_find_entity(const cleora_graph_t *cg, const char *id, int64_t id_len) {
+    Graph *g = const_cast<cleora_graph_t *>(cg);
+    if (g->id_index.empty() && !g->ids.empty())
+        for (size_t i = 0; i < g->ids.size(); ++i) g->id_index.emplace(g->ids[i], (int64_t)i);   // first wins
+    auto it = g->id_index.find(std::string(id, (size_t)id_len));
+    return it == g->id_index.end() ? -1 : it->second;
+}
+
+// ================================================================================================ device-level API
+extern "C" int cleora_dev_graph_prepare(cleora_graph_t *g) { return guarded([&] { device_graph(*g); }); }
+extern "C" int cleora_dev_init(const uint64_t *hash, int64_t n, int64_t d, int64_t seed, float *out, void *stream) {
+    return guarded([&] { launch_init(hash, n, d, seed, out, (cudaStream_t)stream); });
+}
+extern "C" int cleora_dev_spmm(cleora_graph_t *g, int markov, const float *x, int64_t d, float *out,
+                               const float *resid, float alpha, float rw, int normalization, void *stream) {
+    return guarded([&] {
+        check_norm(normalization);
+        DeviceGraph &dg = device_graph(*g);
+        launch_spmm(dg, values_of(dg, markov), x, d, out, resid, alpha, rw, normalization, (cudaStream_t)stream);
+    });
+}
+extern "C" int cleora_dev_normalize(const float *x, int64_t n, int64_t d, int normalization, float *out, void *stream) {
+    return guarded([&] { check_norm(normalization); launch_normalize(x, n, d, normalization, out, (cudaStream_t)stream); });
+}
+extern "C" int cleora_dev_col_sums(const float *x, int64_t n, int64_t d, double *sums, int accumulate, void *stream) {
+    return guarded([&] { launch_col_sums(x, n, d, sums, accumulate != 0, (cudaStream_t)stream); });
+}
+extern "C" int cleora_dev_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov,
+                                        void *stream) {
+    return guarded([&] { launch_centered_gram(x, n, d, mean, cov, (cudaStream_t)stream); });
+}
+extern "C" int cleora_dev_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
+                                       int64_t dout, float *out, void *stream) {
+    return guarded([&] { launch_whiten_apply(x, n, d, mean_f32, T, dout, out, (cudaStream_t)stream); });
+}
+extern "C" int cleora_dev_sq_diff_sum(const float *a, const float *b, int64_t n, int f64_diff, double *result,
+                                      void *stream) {
+    return guarded([&] { launch_sq_diff_sum(a, b, n, f64_diff != 0, result, (cudaStream_t)stream); });
+}
+extern "C" int cleora_whiten_transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T) {
+    return guarded([&] {
+        if (dout <= 0 || dout > d) value_error("n_components must be in [1, d]");
+        transform_from_cov(cov, d, dout, T);
+    });
+}
+
+// ================================================================================================ host-buffer API
+extern "C" int cleora_initialize_deterministically(cleora_graph_t *g, int64_t d, int64_t seed, float *out) {
+    return guarded([&] {
+        if (d < 0) value_error("feature_dim must be non-negative");
+        DeviceGraph &dg = device_graph(*g);
+        if (!dg.hash && g->n_rows) value_error("graph has no entity hashes");
+        const size_t cnt = (size_t)g->n_rows * (size_t)d;
+        DevBuf<float> x(cnt);
+        launch_init(dg.hash, g->n_rows, d, seed, x.p, nullptr);
+        CUDA_TRY(cudaMemcpy(out, x.p, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
+extern "C" int cleora_markov_propagate(cleora_graph_t *g, const float *x, int64_t x_rows, int64_t d, int markov,
+                                       float *out) {
+    return guarded([&] {
+        if (x_rows != g->n_cols)                                                       // src/lib.rs:38-43
+            value_error("Embedding matrix has " + std::to_string(x_rows) + " rows but graph has " +
+                        std::to_string(g->n_cols) + " entities");
+        DeviceGraph &dg = device_graph(*g);
+        const float *val = values_of(dg, markov);
+        DevBuf<float> dx((size_t)x_rows * d), dout((size_t)g->n_rows * d);
+        CUDA_TRY(cudaMemcpy(dx.p, x, dx.n * sizeof(float), cudaMemcpyHostToDevice));
+        launch_spmm(dg, val, dx.p, d, dout.p, nullptr, 1.f, 0.f, CLEORA_NORM_NONE, nullptr);
+        CUDA_TRY(cudaMemcpy(out, dout.p, dout.n * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
+extern "C" int cleora_l2_normalize(const float *x, int64_t n, int64_t d, float *out) {
+    return guarded([&] {
+        require_device();
+        DevBuf<float> dx((size_t)n * d), dy((size_t)n * d);
+        CUDA_TRY(cudaMemcpy(dx.p, x, dx.n * sizeof(float), cudaMemcpyHostToDevice));
+        launch_normalize(dx.p, n, d, CLEORA_NORM_L2_RUST, dy.p, nullptr);
+        CUDA_TRY(cudaMemcpy(out, dy.p, dy.n * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
+// embed_full / embed_full_with_convergence (src/embedding.rs:106-188) on the device: X stays in HBM.
+static void embed_fast_impl(cleora_graph_t *g, int64_t d, int64_t iters, int markov, int64_t seed, float rw,
+                            float threshold, bool with_conv, float *out, int64_t *iters_done) {
+    if (g->n_rows != g->n_cols) value_error("embed needs a full (square) graph, not a row shard");
+    if (d < 0 || iters < 0) value_error("feature_dim and num_iterations must be non-negative");
+    DeviceGraph &dg = device_graph(*g);
+    const float *val = values_of(dg, markov);
+    if (!dg.hash && g->n_rows) value_error("graph has no entity hashes");
+    const int64_t n = g->n_rows;
+    const size_t cnt = (size_t)n * (size_t)d;
+    DevBuf<float> a(cnt), b(cnt);
+    DevBuf<double> dsum(1);
+    float *src = a.p, *dst = b.p;
+    launch_init(dg.hash, n, d, seed, src, nullptr);
+    const bool use_res = rw > 0.0f && rw < 1.0f;                 // embedding.rs:116
+    const float alpha = 1.0f - rw;
+    const bool check = with_conv && threshold > 0.0f;
+    int64_t actual = iters;
+    for (int64_t it = 0; it < iters; ++it) {
+        launch_spmm(dg, val, src, d, dst, use_res ? src : nullptr, alpha, rw, CLEORA_NORM_L2_RUST, nullptr);
+        std::swap(src, dst);                                     // src = newest iterate, dst = previous
+        if (check && it > 0) {
+            launch_sq_diff_sum(src, dst, (int64_t)cnt, false, dsum.p, nullptr);
+            double h = 0.0;
+            CUDA_TRY(cudaMemcpy(&h, dsum.p, sizeof(double), cudaMemcpyDeviceToHost));
+            const float rmse = std::sqrt((float)h / (float)(uint64_t)cnt);
+            if (rmse < threshold) { actual = it + 1; break; }
+        }
+    }
+    CUDA_TRY(cudaMemcpy(out, src, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+    if (iters_done) *iters_done = actual;
+}
+
+extern "C" int cleora_embed_fast(cleora_graph_t *g, int64_t d, int64_t iters, int markov, int64_t seed,
+                                 float residual_weight, float *out) {
+    return guarded([&] { embed_fast_impl(g, d, iters, markov, seed, residual_weight, 0.f, false, out, nullptr); });
+}
+extern "C" int cleora_embed_fast_convergence(cleora_graph_t *g, int64_t d, int64_t max_iters, int markov, int64_t seed,
+                                             float residual_weight, float convergence_threshold, float *out,
+                                             int64_t *iters_done) {
+    return guarded([&] {
+        embed_fast_impl(g, d, max_iters, markov, seed, residual_weight, convergence_threshold, true, out, iters_done);
+    });
+}
+
+extern "C" int cleora_whiten_embeddings(const float *x, int64_t n, int64_t d, int64_t n_components, float *out) {
+    return guarded([&] {
+        require_device();
+        const int64_t dout = n_components > 0 ? n_components : d;
+        if (dout > d) value_error("n_components must be <= feature dimension");
+        if (n <= 1) {                                            // pycleora/__init__.py:132-133
+            if (n == 1) std::memcpy(out, x, sizeof(float) * (size_t)d);
+            return;
+        }
+        DevBuf<float> dx((size_t)n * d), dz((size_t)n * dout);
+        CUDA_TRY(cudaMemcpy(dx.p, x, dx.n * sizeof(float), cudaMemcpyHostToDevice));
+        WhitenState ws;
+        Phase ph;
+        whiten_device(dx.p, n, d, dout, dz.p, ws, nullptr, ph);
+        CUDA_TRY(cudaMemcpy(out, dz.p, dz.n * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
+// The Python loop of embed() (pycleora/__init__.py:97-125), device-resident.
+extern "C" int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64_t iters, int markov, int64_t seed,
+                            double residual_weight, double convergence_threshold, int normalization, int whiten,
+                            float *out, int64_t *iters_done, double *timings_ms) {
+    return guarded([&] {
+        check_norm(normalization);
+        if (g->n_rows != g->n_cols) value_error("embed needs a full (square) graph, not a row shard");
+        if (d < 0 || iters < 0) value_error("feature_dim and num_iterations must be non-negative");
+        DeviceGraph &dg = device_graph(*g);
+        const float *val = values_of(dg, markov);
+        const int64_t n = g->n_rows;
+        const size_t cnt = (size_t)n * (size_t)d;
+        Phase ph;
+        ph.on = timings_ms != nullptr;
+        if (timings_ms) std::fill(timings_ms, timings_ms + 8, 0.0);
+        const bool conv = convergence_threshold > 0.0;
+        const bool do_whiten = whiten != 0 && n > 1;
+        DevBuf<float> bx(cnt), by(cnt), bw;
+        if (conv && do_whiten) bw.alloc(cnt);
+        DevBuf<double> dsum(1);
+        float *cur = bx.p, *y = by.p, *w = bw.p;
+        if (x0) {
+            ph.begin();
+            CUDA_TRY(cudaMemcpyAsync(cur, x0, cnt * sizeof(float), cudaMemcpyHostToDevice, nullptr));
+            ph.end(PH_H2D);
+        } else {
+            if (!dg.hash && n) value_error("graph has no entity hashes");
+            ph.begin();
+            launch_init(dg.hash, n, d, seed, cur, nullptr);
+            ph.end(PH_INIT);
+        }
+        const bool use_res = residual_weight > 0.0;              // pycleora/__init__.py:114 (no < 1 guard)
+        const float alpha = (float)(1.0 - residual_weight), rwf = (float)residual_weight;
+        WhitenState ws;
+        int64_t done = 0;
+        float *result = cur;
+        for (int64_t it = 0; it < iters; ++it) {
+            ph.begin();
+            launch_spmm(dg, val, cur, d, y, use_res ? cur : nullptr, alpha, rwf, normalization, nullptr);
+            ph.end(PH_SPMM);
+            float *fresh;
+            if (do_whiten) {
+                fresh = conv ? w : cur;                          // without rmse the old iterate can be overwritten
+                whiten_device(y, n, d, d, fresh, ws, nullptr, ph);
+            } else {
+                fresh = y;
+            }
+            done = it + 1;
+            bool stop = false;
+            if (conv && it > 0) {                                // _compute_rmse, pycleora/__init__.py:974-976
+                ph.begin();
+                launch_sq_diff_sum(fresh, cur, (int64_t)cnt, true, dsum.p, nullptr);
+                double h = 0.0;
+                CUDA_TRY(cudaMemcpy(&h, dsum.p, sizeof(double), cudaMemcpyDeviceToHost));
+                ph.end(PH_RMSE);
+                stop = std::sqrt(h / (double)cnt) < convergence_threshold;
+            }
+            if (fresh == w) std::swap(cur, w);
+            else if (fresh == y) std::swap(cur, y);
+            result = cur;
+            if (stop) break;
+        }
+        ph.begin();
+        CUDA_TRY(cudaMemcpyAsync(out, result, cnt * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
+        ph.end(PH_D2H);
+        CUDA_TRY(cudaStreamSynchronize(nullptr));
+        ph.collect(timings_ms);
+        if (iters_done) *iters_done = done;
+    });
+}

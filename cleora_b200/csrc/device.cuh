@@ -1,0 +1,73 @@
+// Internal device-side declarations of libcleora_b200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <string>
+
+namespace cleora {
+
+// Device image of a Graph: SoA CSR (8 B/nnz streamed per SpMM instead of the reference's 12 B AoS Edge,
+// src/sparse_matrix.rs:73-78) with 64-bit row offsets (nnz of the 1.5 B-edge config exceeds 2^31).
+struct DeviceGraph {
+    int device = -1;
+    int64_t n_rows = 0, n_cols = 0, nnz = 0, row_offset = 0;
+    int64_t *rowptr = nullptr;
+    uint32_t *col = nullptr;
+    float *left = nullptr, *sym = nullptr;
+    uint64_t *hash = nullptr;
+    // long-row schedule (rows with more than LONG_ROW_EDGES edges are split across warps)
+    int64_t n_long = 0;
+    int32_t *long_rows = nullptr;
+};
+
+void set_error(const std::string &msg);
+extern std::atomic<int64_t> g_launches;
+
+struct CudaFail {
+    std::string msg;
+};
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            throw ::cleora::CudaFail{std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                                     ":" + std::to_string(__LINE__) + ")"};                              \
+    } while (0)
+
+#define LAUNCH_CHECK()                             \
+    do {                                           \
+        ::cleora::g_launches.fetch_add(1);         \
+        CUDA_TRY(cudaGetLastError());              \
+    } while (0)
+
+// Growable device scratch, one per host thread and purpose.
+struct Scratch {
+    void *p = nullptr;
+    size_t cap = 0;
+    int device = -1;
+    void *get(size_t bytes);
+    void release();
+};
+struct Workspace {
+    Scratch colsum_partials, gram_partials, sqdiff_partials, misc;
+    size_t bytes() const { return colsum_partials.cap + gram_partials.cap + sqdiff_partials.cap + misc.cap; }
+};
+Workspace &workspace();
+
+// ---- launchers (kernels.cu); all enqueue on `st` and throw CudaFail on launch errors -------------------
+void launch_init(const uint64_t *hash, int64_t n, int64_t d, int64_t seed, float *out, cudaStream_t st);
+void launch_spmm(const DeviceGraph &g, const float *val, const float *x, int64_t d, float *out, const float *resid,
+                 float alpha, float rw, int norm, cudaStream_t st);
+void launch_normalize(const float *x, int64_t n, int64_t d, int norm, float *out, cudaStream_t st);
+void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool accumulate, cudaStream_t st);
+void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st);
+void launch_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
+                         float *out, cudaStream_t st);
+void launch_sq_diff_sum(const float *a, const float *b, int64_t n, bool f64_diff, double *result, cudaStream_t st);
+void launch_scale_f64(double *v, int64_t n, double factor, cudaStream_t st);
+void launch_f64_to_f32(const double *in, float *out, int64_t n, cudaStream_t st);
+
+}  // namespace cleora

@@ -1,0 +1,607 @@
+// sm_100a kernels of libcleora_b200.
+//
+//   K0 init_kernel            deterministic init                     src/lib.rs:69-81,478-488
+//   K1 spmm_rows_kernel       CSR x dense SpMM + residual + row norm src/embedding.rs:52-104,121-131,
+//                                                                    pycleora/__init__.py:114-115,943-950
+//   K2 col_sums / gram_f64    column mean, centred covariance (f64)  pycleora/__init__.py:136-143
+//   K3 whiten_apply_kernel    (X - mean) @ T in f32                  pycleora/__init__.py:157-163
+//      sq_diff                rmse numerator                         src/embedding.rs:169-177, __init__.py:974-976
+//
+// Numerical contract of K1: per output element the products are accumulated in the row's stored (column)
+// order with a separate f32 multiply and f32 add (__fmul_rn/__fadd_rn, no FMA contraction) -- the exact
+// operation sequence of the reference's spmm_kernel, so the un-normalised SpMM is bit-identical to the CPU path.
+// All of these are HBM-bound gather/stream kernels: no tensor cores here by design.
+#include "device.cuh"
+#include "../../include/cleora_b200.h"
+
+#include <algorithm>
+
+namespace cleora {
+
+static constexpr unsigned FULL = 0xffffffffu;
+
+// ================================================================================================ K0
+__global__ void init_kernel(const uint64_t *__restrict__ hash, int64_t n, int64_t d, int64_t seed,
+                            float *__restrict__ out) {
+    const int64_t total = n * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / d, j = i - r * d;
+        const uint64_t num = hash[r] + (uint64_t)j + (uint64_t)seed;          // wrapping i64 adds
+        const int64_t hashed = (int64_t)(num * 0x517cc1b727220a95ULL);       // FxHasher::write_i64 from zero state
+        out[i] = (float)(hashed % 8388608LL) / 8388608.0f;                     // % keeps the dividend's sign
+    }
+}
+
+void launch_init(const uint64_t *hash, int64_t n, int64_t d, int64_t seed, float *out, cudaStream_t st) {
+    if (n * d == 0) return;
+    const int threads = 256;
+    const int64_t blocks = std::min<int64_t>((n * d + threads - 1) / threads, 148 * 32);
+    init_kernel<<<(unsigned)blocks, threads, 0, st>>>(hash, n, d, seed, out);
+    LAUNCH_CHECK();
+}
+
+// ================================================================================================ K1
+__device__ __forceinline__ float group_sum(float v, int width) {
+    for (int off = width >> 1; off > 0; off >>= 1) v = __fadd_rn(v, __shfl_xor_sync(FULL, v, off));
+    return v;
+}
+
+// Row-norm epilogue shared by the SpMM kernels: `a` holds this lane's NV values of the row, `part` the lane's
+// partial (sum of squares or of |x|) already reduced over the lane group.
+__device__ __forceinline__ float norm_scale_factor(float part, int norm) {
+    float nrm = (norm == CLEORA_NORM_L1_NUMPY) ? part : sqrtf(part);
+    return fmaxf(nrm, 1e-10f);
+}
+
+// LPR lanes cooperate on one row (32/LPR rows per warp); each lane owns VEC float4 column groups, so
+// D = 4*LPR*VEC.  Edge (col,val) pairs are fetched LPR at a time with one coalesced load per lane and broadcast
+// by shuffle; X rows are read with 128-bit read-only loads, U rows in flight before the first dependent add.
+template <int LPR, int VEC, int U>
+__global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restrict__ rowptr,
+                                                        const uint32_t *__restrict__ col,
+                                                        const float *__restrict__ val, const float *__restrict__ x,
+                                                        float *__restrict__ out, const float *__restrict__ resid,
+                                                        int64_t n_rows, float alpha, float rw, int norm) {
+    constexpr int D4 = LPR * VEC;          // float4 per row
+    constexpr int RPW = 32 / LPR;          // rows per warp
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LPR - 1);
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t row = warp * RPW + lane / LPR;
+    const bool valid = row < n_rows;
+    int64_t s = 0, e = 0;
+    if (valid) { s = rowptr[row]; e = rowptr[row + 1]; }
+
+    float4 acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 *__restrict__ xv = reinterpret_cast<const float4 *>(x);
+
+    for (int64_t base = s; __any_sync(FULL, base < e); base += LPR) {
+        const int64_t rem = e - base;
+        const int cnt = rem > LPR ? LPR : (int)rem;            // <= 0 for groups that are already done
+        uint32_t my_c = 0;
+        float my_v = 0.f;
+        if (gl < cnt) { my_c = __ldg(col + base + gl); my_v = __ldg(val + base + gl); }
+#pragma unroll 1
+        for (int k = 0; k < LPR; k += U) {
+            if (!__any_sync(FULL, k < cnt)) break;
+            float4 xr[U][VEC];
+            float vv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t c = __shfl_sync(FULL, my_c, k + u, LPR);
+                vv[u] = __shfl_sync(FULL, my_v, k + u, LPR);
+                if (k + u < cnt) {
+                    const float4 *p = xv + (int64_t)c * D4 + gl;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) xr[u][v] = __ldg(p + v * LPR);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (k + u < cnt) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        acc[v].x = __fadd_rn(acc[v].x, __fmul_rn(vv[u], xr[u][v].x));
+                        acc[v].y = __fadd_rn(acc[v].y, __fmul_rn(vv[u], xr[u][v].y));
+                        acc[v].z = __fadd_rn(acc[v].z, __fmul_rn(vv[u], xr[u][v].z));
+                        acc[v].w = __fadd_rn(acc[v].w, __fmul_rn(vv[u], xr[u][v].w));
+                    }
+                }
+            }
+        }
+    }
+
+    if (resid != nullptr && valid) {                    // dst = alpha*dst + rw*src (embedding.rs:121-129)
+        const float4 *rp = reinterpret_cast<const float4 *>(resid) + row * D4 + gl;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const float4 r = __ldg(rp + v * LPR);
+            acc[v].x = __fadd_rn(__fmul_rn(alpha, acc[v].x), __fmul_rn(rw, r.x));
+            acc[v].y = __fadd_rn(__fmul_rn(alpha, acc[v].y), __fmul_rn(rw, r.y));
+            acc[v].z = __fadd_rn(__fmul_rn(alpha, acc[v].z), __fmul_rn(rw, r.z));
+            acc[v].w = __fadd_rn(__fmul_rn(alpha, acc[v].w), __fmul_rn(rw, r.w));
+        }
+    }
+
+    if (norm != CLEORA_NORM_NONE) {
+        float part = 0.f;
+        if (norm == CLEORA_NORM_L1_NUMPY) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                part = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(part, fabsf(acc[v].x)), fabsf(acc[v].y)), fabsf(acc[v].z)), fabsf(acc[v].w));
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                part = __fadd_rn(part, __fmul_rn(acc[v].x, acc[v].x));
+                part = __fadd_rn(part, __fmul_rn(acc[v].y, acc[v].y));
+                part = __fadd_rn(part, __fmul_rn(acc[v].z, acc[v].z));
+                part = __fadd_rn(part, __fmul_rn(acc[v].w, acc[v].w));
+            }
+        }
+        part = group_sum(part, LPR);
+        const float nrm = norm_scale_factor(part, norm);
+        if (norm == CLEORA_NORM_L2_RUST) {
+            const float inv = __fdiv_rn(1.0f, nrm);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                acc[v].x = __fmul_rn(acc[v].x, inv); acc[v].y = __fmul_rn(acc[v].y, inv);
+                acc[v].z = __fmul_rn(acc[v].z, inv); acc[v].w = __fmul_rn(acc[v].w, inv);
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                acc[v].x = __fdiv_rn(acc[v].x, nrm); acc[v].y = __fdiv_rn(acc[v].y, nrm);
+                acc[v].z = __fdiv_rn(acc[v].z, nrm); acc[v].w = __fdiv_rn(acc[v].w, nrm);
+            }
+        }
+    }
+    if (valid) {
+        float4 *op = reinterpret_cast<float4 *>(out) + row * D4 + gl;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) op[v * LPR] = acc[v];
+    }
+}
+
+// Any d: one warp per row, lane owns columns lane, lane+32, ... in passes of T*32 columns.  Same accumulation
+// order as above.  With more than one pass the row is written un-normalised first and rescaled afterwards.
+template <int T>
+__global__ void __launch_bounds__(256) spmm_generic_kernel(const int64_t *__restrict__ rowptr,
+                                                           const uint32_t *__restrict__ col,
+                                                           const float *__restrict__ val, const float *__restrict__ x,
+                                                           float *__restrict__ out, const float *__restrict__ resid,
+                                                           int64_t n_rows, int d, float alpha, float rw, int norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;                                     // whole warp exits together
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+    float part = 0.f;
+    for (int c0 = 0; c0 < d; c0 += T * 32) {
+        float acc[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[t] = 0.f;
+        for (int64_t base = s; base < e; base += 32) {
+            const int cnt = (e - base) > 32 ? 32 : (int)(e - base);
+            uint32_t my_c = 0;
+            float my_v = 0.f;
+            if (lane < cnt) { my_c = __ldg(col + base + lane); my_v = __ldg(val + base + lane); }
+            for (int k = 0; k < cnt; ++k) {
+                const uint32_t c = __shfl_sync(FULL, my_c, k);
+                const float v = __shfl_sync(FULL, my_v, k);
+                const float *xr = x + (int64_t)c * d + c0 + lane;
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                    if (c0 + t * 32 + lane < d) acc[t] = __fadd_rn(acc[t], __fmul_rn(v, __ldg(xr + t * 32)));
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int j = c0 + t * 32 + lane;
+            if (j < d) {
+                float a = acc[t];
+                if (resid != nullptr) a = __fadd_rn(__fmul_rn(alpha, a), __fmul_rn(rw, __ldg(resid + row * d + j)));
+                part = __fadd_rn(part, norm == CLEORA_NORM_L1_NUMPY ? fabsf(a) : __fmul_rn(a, a));
+                out[row * d + j] = a;
+            }
+        }
+    }
+    if (norm == CLEORA_NORM_NONE) return;
+    part = group_sum(part, 32);
+    const float nrm = norm_scale_factor(part, norm);
+    const float inv = __fdiv_rn(1.0f, nrm);
+    __syncwarp();
+    for (int j = lane; j < d; j += 32) {
+        const float a = out[row * d + j];
+        out[row * d + j] = (norm == CLEORA_NORM_L2_RUST) ? __fmul_rn(a, inv) : __fdiv_rn(a, nrm);
+    }
+}
+
+template <int LPR, int VEC, int U>
+static void launch_rows(const DeviceGraph &g, const float *val, const float *x, float *out, const float *resid,
+                        float alpha, float rw, int norm, cudaStream_t st) {
+    constexpr int RPW = 32 / LPR;
+    const int threads = 256;
+    const int64_t rows_per_block = (int64_t)(threads / 32) * RPW;
+    const int64_t blocks = (g.n_rows + rows_per_block - 1) / rows_per_block;
+    spmm_rows_kernel<LPR, VEC, U><<<(unsigned)blocks, threads, 0, st>>>(g.rowptr, g.col, val, x, out, resid,
+                                                                        g.n_rows, alpha, rw, norm);
+    LAUNCH_CHECK();
+}
+
+void launch_spmm(const DeviceGraph &g, const float *val, const float *x, int64_t d, float *out, const float *resid,
+                 float alpha, float rw, int norm, cudaStream_t st) {
+    if (g.n_rows == 0 || d == 0) return;
+    if (g.n_rows > (int64_t)0x7fffffff * 8) throw CudaFail{"too many rows for one launch"};
+    switch (d) {
+        case 8:    launch_rows<2, 1, 2>(g, val, x, out, resid, alpha, rw, norm, st); return;
+        case 16:   launch_rows<4, 1, 4>(g, val, x, out, resid, alpha, rw, norm, st); return;
+        case 32:   launch_rows<8, 1, 8>(g, val, x, out, resid, alpha, rw, norm, st); return;
+        case 64:   launch_rows<16, 1, 8>(g, val, x, out, resid, alpha, rw, norm, st); return;
+        case 96:   launch_rows<8, 3, 4>(g, val, x, out, resid, alpha, rw, norm, st); return;
+        case 128:  launch_rows<32, 1, 8>(g, val, x, out, resid, alpha, rw, norm, st); return;
+        case 192:  launch_rows<16, 3, 4>(g, val, x, out, resid, alpha, rw, norm, st); return;
+        case 256:  launch_rows<32, 2, 4>(g, val, x, out, resid, alpha, rw, norm, st); return;
+        case 384:  launch_rows<32, 3, 4>(g, val, x, out, resid, alpha, rw, norm, st); return;
+        case 512:  launch_rows<32, 4, 4>(g, val, x, out, resid, alpha, rw, norm, st); return;
+        case 1024: launch_rows<32, 8, 2>(g, val, x, out, resid, alpha, rw, norm, st); return;
+        default: break;
+    }
+    const int threads = 256;
+    const int64_t blocks = (g.n_rows + 7) / 8;
+    spmm_generic_kernel<8><<<(unsigned)blocks, threads, 0, st>>>(g.rowptr, g.col, val, x, out, resid, g.n_rows,
+                                                                 (int)d, alpha, rw, norm);
+    LAUNCH_CHECK();
+}
+
+// Row normalisation alone: warp per row, two passes over the row (second pass hits L1/L2).
+__global__ void __launch_bounds__(256) normalize_kernel(const float *__restrict__ x, int64_t n, int d, int norm,
+                                                        float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float *xr = x + row * d;
+    float part = 0.f;
+    for (int j = lane; j < d; j += 32) {
+        const float a = xr[j];
+        part = __fadd_rn(part, norm == CLEORA_NORM_L1_NUMPY ? fabsf(a) : __fmul_rn(a, a));
+    }
+    part = group_sum(part, 32);
+    const float nrm = norm_scale_factor(part, norm);
+    const float inv = __fdiv_rn(1.0f, nrm);
+    for (int j = lane; j < d; j += 32) {
+        const float a = xr[j];
+        out[row * d + j] = norm == CLEORA_NORM_NONE ? a : (norm == CLEORA_NORM_L2_RUST ? __fmul_rn(a, inv) : __fdiv_rn(a, nrm));
+    }
+}
+
+void launch_normalize(const float *x, int64_t n, int64_t d, int norm, float *out, cudaStream_t st) {
+    if (n * d == 0) return;
+    normalize_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x, n, (int)d, norm, out);
+    LAUNCH_CHECK();
+}
+
+// ================================================================================================ K2a column sums
+// Stage 1: every warp of the grid walks rows warp, warp+W, ... and keeps f64 partial sums of its columns
+// (lane owns columns lane, lane+32, ...).  Stage 2: one thread per column adds the W partials in warp order.
+// Deterministic for a fixed launch shape.
+template <int T>
+__global__ void __launch_bounds__(256) col_sums_stage1(const float *__restrict__ x, int64_t n, int d, int c0,
+                                                       double *__restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const int64_t W = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    double acc[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t] = 0.0;
+    for (int64_t r = w; r < n; r += W) {
+        const float *xr = x + r * d + c0 + lane;
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+            if (c0 + t * 32 + lane < d) acc[t] += (double)__ldg(xr + t * 32);
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+        if (c0 + t * 32 + lane < d) partial[w * d + c0 + t * 32 + lane] = acc[t];
+}
+
+__global__ void col_sums_stage2(const double *__restrict__ partial, int64_t W, int d, double *__restrict__ sums,
+                                int accumulate) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    double s = 0.0;
+    for (int64_t w = 0; w < W; ++w) s += partial[w * d + j];
+    sums[j] = accumulate ? sums[j] + s : s;
+}
+
+void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool accumulate, cudaStream_t st) {
+    if (d == 0) return;
+    const int threads = 256;
+    int64_t blocks = std::min<int64_t>((n + 7) / 8, 148 * 4);
+    if (blocks < 1) blocks = 1;
+    const int64_t W = blocks * (threads / 32);
+    double *partial = (double *)workspace().colsum_partials.get(size_t(W) * size_t(d) * sizeof(double));
+    for (int c0 = 0; c0 < (int)d; c0 += 8 * 32) {
+        col_sums_stage1<8><<<(unsigned)blocks, threads, 0, st>>>(x, n, (int)d, c0, partial);
+        LAUNCH_CHECK();
+    }
+    col_sums_stage2<<<(unsigned)((d + 127) / 128), 128, 0, st>>>(partial, W, (int)d, sums, accumulate ? 1 : 0);
+    LAUNCH_CHECK();
+}
+
+// ================================================================================================ K2b centred Gram, f64
+// cov = sum_r (x_r - mean)(x_r - mean)^T in IEEE f64 (the reference accumulates the covariance in f64,
+// pycleora/__init__.py:138-142; the PCA eigenbasis is sensitive to ~1/eigengap, so lower precision is not an
+// option).  FP64 tensor-core path: mma.sync m8n8k4 f64 (DMMA) -- tcgen05 has no f64 kind.
+// One CTA = one 64x64 block (bi <= bj) of the d x d matrix for one slice of rows; partial blocks are reduced in
+// slice order by gram_reduce (deterministic).
+static constexpr int GB = 64;     // block edge
+static constexpr int GK = 32;     // rows per staged chunk
+static constexpr int GLD = 68;    // smem leading dimension in doubles (68 mod 16 == 4: conflict-free fragments)
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) gram_f64_kernel(const float *__restrict__ x, int64_t n, int d,
+                                                       const double *__restrict__ mean, double *__restrict__ partial,
+                                                       int nblk, int64_t rows_per_slice) {
+    __shared__ double As[GK][GLD];
+    __shared__ double Bs[GK][GLD];
+    // decode (bi, bj), bi <= bj, from the linear pair index
+    int bi = 0, rest = blockIdx.x;
+    while (rest >= nblk - bi) { rest -= nblk - bi; ++bi; }
+    const int bj = bi + rest;
+    const bool diag = bi == bj;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice;
+    const int64_t r1 = min(n, r0 + rows_per_slice);
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wm = w >> 2, wn = w & 3;                 // warp tile: rows wm*32.., cols wn*16..
+    double acc[4][2][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    // staging map: thread -> (row lr + 16*i, 4 consecutive columns lc..lc+3) of the 32x64 chunk
+    const int lr = tid >> 4, lc = (tid & 15) * 4;
+    const int ca = bi * GB + lc, cb = bj * GB + lc;
+    double ma[4], mb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        ma[q] = (ca + q < d) ? mean[ca + q] : 0.0;
+        mb[q] = (cb + q < d) ? mean[cb + q] : 0.0;
+    }
+    float ra[2][4], rb[2][4];
+    auto fetch = [&](int64_t rbase) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int64_t r = rbase + lr + 16 * i;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ra[i][q] = (r < r1 && ca + q < d) ? __ldg(x + r * d + ca + q) : 0.f;
+                if (!diag) rb[i][q] = (r < r1 && cb + q < d) ? __ldg(x + r * d + cb + q) : 0.f;
+            }
+        }
+    };
+    auto stage = [&](int64_t rbase) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int64_t r = rbase + lr + 16 * i;
+            const bool in = r < r1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                As[lr + 16 * i][lc + q] = (in && ca + q < d) ? (double)ra[i][q] - ma[q] : 0.0;
+                if (!diag) Bs[lr + 16 * i][lc + q] = (in && cb + q < d) ? (double)rb[i][q] - mb[q] : 0.0;
+            }
+        }
+    };
+
+    if (r0 < r1) fetch(r0);
+    for (int64_t rb0 = r0; rb0 < r1; rb0 += GK) {
+        __syncthreads();                       // previous chunk fully consumed
+        stage(rb0);
+        __syncthreads();
+        if (rb0 + GK < r1) fetch(rb0 + GK);    // prefetch next chunk into registers while computing
+        const double(*Bp)[GLD] = diag ? As : Bs;
+#pragma unroll
+        for (int kk = 0; kk < GK / 4; ++kk) {
+            const int kr = kk * 4 + (lane & 3);
+            double a[4], b[2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = As[kr][wm * 32 + mi * 8 + (lane >> 2)];
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) b[ni] = Bp[kr][wn * 16 + ni * 8 + (lane >> 2)];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+    double *P = partial + (int64_t)blockIdx.y * d * d;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int gr = bi * GB + wm * 32 + mi * 8 + (lane >> 2);
+                const int gc = bj * GB + wn * 16 + ni * 8 + (lane & 3) * 2 + j;
+                if (gr < d && gc < d) P[(int64_t)gr * d + gc] = acc[mi][ni][j];
+            }
+}
+
+// cov[i][j] = cov[j][i] = sum over slices, for block-upper (i-block <= j-block) entries.
+__global__ void gram_reduce_kernel(const double *__restrict__ partial, int slices, int d, double *__restrict__ cov) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)d * d) return;
+    const int i = (int)(idx / d), j = (int)(idx - (int64_t)i * d);
+    if (i / GB > j / GB) return;
+    double s = 0.0;
+    for (int k = 0; k < slices; ++k) s += partial[(int64_t)k * d * d + idx];
+    cov[idx] = s;
+    if (i / GB != j / GB) cov[(int64_t)j * d + i] = s;
+}
+
+void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st) {
+    if (d == 0) return;
+    const int nblk = (int)((d + GB - 1) / GB);
+    const int npairs = nblk * (nblk + 1) / 2;
+    int64_t slices = std::max<int64_t>(1, std::min<int64_t>((n + 4 * GK - 1) / (4 * GK), (148 * 6) / npairs));
+    slices = std::min<int64_t>(slices, 65535);
+    const int64_t rows_per_slice = std::max<int64_t>(GK, ((n + slices - 1) / slices + GK - 1) / GK * GK);
+    slices = std::max<int64_t>(1, (n + rows_per_slice - 1) / rows_per_slice);
+    double *partial = (double *)workspace().gram_partials.get(size_t(slices) * size_t(d) * size_t(d) * sizeof(double));
+    dim3 grid((unsigned)npairs, (unsigned)slices);
+    gram_f64_kernel<<<grid, 256, 0, st>>>(x, n, (int)d, mean, partial, nblk, rows_per_slice);
+    LAUNCH_CHECK();
+    const int64_t tot = d * d;
+    gram_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(partial, (int)slices, (int)d, cov);
+    LAUNCH_CHECK();
+}
+
+// ================================================================================================ K3 whiten apply
+// out[n, dout] = (x - mean_f32) @ T, f32 FMA accumulation in k order.  128x128x8 register-tiled SGEMM
+// (8x8 per thread); the centring is applied while staging the A tile.
+static constexpr int AM = 128, AN = 128, AK = 8;
+
+__global__ void __launch_bounds__(256) whiten_apply_kernel(const float *__restrict__ x, int64_t n, int d,
+                                                           const float *__restrict__ mean, const float *__restrict__ T,
+                                                           int dout, float *__restrict__ out) {
+    __shared__ __align__(16) float As[AK][AM + 4];
+    __shared__ __align__(16) float Bs[AK][AN + 4];
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * AM;
+    const int col0 = blockIdx.y * AN;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int a_r = tid >> 1, a_k = (tid & 1) * 4;      // A tile: 128 rows x 8 k, 4 consecutive k per thread
+    const int b_k = tid >> 5, b_c = (tid & 31) * 4;     // B tile: 8 k x 128 cols, 4 consecutive cols per thread
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
+        const int64_t r = row0 + a_r;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + a_k + q;
+            ra[q] = (r < n && k < d) ? __ldg(x + r * d + k) - __ldg(mean + k) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + b_k, c = col0 + b_c + q;
+            rb[q] = (k < d && c < dout) ? __ldg(T + (int64_t)k * dout + c) : 0.f;
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < d; k0 += AK) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { As[a_k + q][a_r] = ra[q]; Bs[b_k][b_c + q] = rb[q]; }
+        __syncthreads();
+        if (k0 + AK < d) fetch(k0 + AK);
+#pragma unroll
+        for (int k = 0; k < AK; ++k) {
+            // thread owns rows {ty*4..+3, 64+ty*4..+3} x cols {tx*4..+3, 64+tx*4..+3}: 128-bit conflict-free LDS
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[k][64 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (r >= n) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (c < dout) out[r * dout + c] = acc[i][j];
+        }
+    }
+}
+
+void launch_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
+                         float *out, cudaStream_t st) {
+    if (n == 0 || dout == 0) return;
+    dim3 grid((unsigned)((n + AM - 1) / AM), (unsigned)((dout + AN - 1) / AN));
+    whiten_apply_kernel<<<grid, 256, 0, st>>>(x, n, (int)d, mean_f32, T, (int)dout, out);
+    LAUNCH_CHECK();
+}
+
+// ================================================================================================ rmse numerator
+// f64_diff == 0: Rust semantics (f32 difference and square, src/embedding.rs:173-174); == 1: numpy semantics
+// (difference and square in f64, pycleora/__init__.py:975-976).  The SUM is f64 and tree-shaped in both cases
+// (the reference's serial f32 running sum cannot be reproduced in parallel).
+__global__ void __launch_bounds__(256) sq_diff_stage1(const float *__restrict__ a, const float *__restrict__ b,
+                                                      int64_t n, int f64_diff, double *__restrict__ partial) {
+    __shared__ double sh[8];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (f64_diff) {
+            const double dl = (double)a[i] - (double)b[i];
+            acc += dl * dl;
+        } else {
+            const float dl = __fsub_rn(a[i], b[i]);
+            acc += (double)__fmul_rn(dl, dl);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += sh[w];
+        partial[blockIdx.x] = s;
+    }
+}
+__global__ void sq_diff_stage2(const double *__restrict__ partial, int nb, double *__restrict__ result) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < nb; ++i) s += partial[i];
+        result[0] = s;
+    }
+}
+
+void launch_sq_diff_sum(const float *a, const float *b, int64_t n, bool f64_diff, double *result, cudaStream_t st) {
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 8));
+    double *partial = (double *)workspace().sqdiff_partials.get(size_t(blocks) * sizeof(double));
+    sq_diff_stage1<<<blocks, 256, 0, st>>>(a, b, n, f64_diff ? 1 : 0, partial);
+    LAUNCH_CHECK();
+    sq_diff_stage2<<<1, 32, 0, st>>>(partial, blocks, result);
+    LAUNCH_CHECK();
+}
+
+// ================================================================================================ small helpers
+__global__ void scale_f64_kernel(double *v, int64_t n, double f) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] *= f;
+}
+void launch_scale_f64(double *v, int64_t n, double factor, cudaStream_t st) {
+    if (n == 0) return;
+    scale_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, n, factor);
+    LAUNCH_CHECK();
+}
+__global__ void f64_to_f32_kernel(const double *in, float *out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+void launch_f64_to_f32(const double *in, float *out, int64_t n, cudaStream_t st) {
+    if (n == 0) return;
+    f64_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+    LAUNCH_CHECK();
+}
+
+}  // namespace cleora

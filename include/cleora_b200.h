@@ -1,0 +1,186 @@
+/*
+ * cleora_b200.h -- C ABI of libcleora_b200.so, the B200-native replacement for pycleora's hot path
+ *   SparseMatrix::{left,symmetric}_markov_propagate -> row L2-normalise -> whiten_embeddings, wrapped by embed().
+ *
+ * This is the drop-in boundary: plain pointers and sizes, integer status returns, no exceptions and no
+ * torch / numpy / pybind types.  It is what the reference's Rust host code (src/lib.rs #[pymethods]) would
+ * bind through `extern "C"` instead of calling src/embedding.rs / src/sparse_matrix_builder.rs; the
+ * reference-side binding is shown in INTEGRATION.md, and cleora_b200/pycleora.py is the same binding written
+ * with ctypes (this image has no Rust toolchain).
+ *
+ * Conventions
+ *   - every function returning `int` returns CLEORA_OK (0) or an error class; the message is available from
+ *     cleora_last_error() (thread-local).  CLEORA_ERR_VALUE maps to Python ValueError, CLEORA_ERR_RUNTIME to
+ *     RuntimeError -- the same classes the reference raises (src/lib.rs:39-42,186-189,220,335-338,465,472).
+ *   - host-buffer entry points ("cleora_*") take HOST pointers owned by the caller; the library owns all
+ *     device memory, copies in/out inside the call, and never aliases caller memory in results
+ *     (the reference returns fresh numpy copies: src/lib.rs:46,251,363).
+ *   - device-level entry points ("cleora_dev_*") take DEVICE pointers plus a cudaStream_t passed as void*;
+ *     they only enqueue work.  They exist so a row-sharded multi-GPU loop (one process per GPU, collectives by
+ *     torch.distributed/NCCL) is composed from the same kernels.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with CLEORA_ERR_CUDA.
+ *   - matrices are C-contiguous row-major float32 [rows, d].
+ */
+#ifndef CLEORA_B200_H
+#define CLEORA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLEORA_OK 0
+#define CLEORA_ERR_VALUE 1   /* bad argument / shape / columns / unknown entity  -> ValueError   */
+#define CLEORA_ERR_RUNTIME 2 /* (de)serialisation, internal invariant            -> RuntimeError */
+#define CLEORA_ERR_CUDA 3    /* CUDA runtime error or no device                  -> RuntimeError */
+
+/* MarkovType, src/embedding.rs:7-10 */
+#define CLEORA_MARKOV_LEFT 0
+#define CLEORA_MARKOV_SYMMETRIC 1
+
+/* Row normalisation fused into the SpMM epilogue.
+ *   L2_RUST  : x * (1 / max(sqrt(sum x^2), 1e-10))        src/embedding.rs:88-104 (embed_fast path)
+ *   L2_NUMPY : x / max(sqrt(sum x^2), 1e-10)              pycleora/__init__.py:943-946 (default embed() path)
+ *   L1_NUMPY : x / max(sum |x|, 1e-10)                    pycleora/__init__.py:947-950 */
+#define CLEORA_NORM_NONE 0
+#define CLEORA_NORM_L2_RUST 1
+#define CLEORA_NORM_L2_NUMPY 2
+#define CLEORA_NORM_L1_NUMPY 3
+
+typedef struct cleora_graph cleora_graph_t; /* opaque: host CSR + entity tables + lazily built device copy */
+
+const char *cleora_last_error(void);
+const char *cleora_version(void);
+/* Number of visible CUDA devices (0 when none / driver missing); never fails. */
+int cleora_device_count(void);
+/* Device used by subsequently created device state of this thread (cudaSetDevice). */
+int cleora_set_device(int device);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Graph construction.  Replaces SparseMatrix::from_iterator (src/lib.rs:104-135) / from_files (:137-173) and
+ * everything below them (src/pipeline.rs, src/entity.rs, src/sparse_matrix_builder.rs, src/configuration.rs).
+ * CSR semantics are bit-exact with the reference for single-buffer accumulation order.
+ * ------------------------------------------------------------------------------------------------------- */
+/* `buf` holds n_lines UTF-8 strings back to back, line i = buf[offsets[i] .. offsets[i+1]). */
+int cleora_graph_from_lines(const char *buf, const int64_t *offsets, int64_t n_lines, const char *columns,
+                            int64_t hyperedge_trim_n, cleora_graph_t **out);
+/* Only .tsv / .csv / .txt paths (src/lib.rs:148-158); empty lines skipped (src/pipeline.rs:212-214). */
+int cleora_graph_from_files(const char *const *paths, int64_t n_paths, const char *columns,
+                            int64_t hyperedge_trim_n, cleora_graph_t **out);
+/* Direct integer ingest: the graph that `from_iterator(("{u} {v}" for u,v in pairs),
+ * "complex::reflexive::<name>")` builds, without strings: entity index = first appearance, entity id =
+ * decimal string of the integer, every pair adds 1/4+1/4 to M[u,v], M[v,u], M[u,u], M[v,v].  u == v pairs are
+ * legal (they add 1 to M[u,u]). */
+int cleora_graph_from_pairs(const uint32_t *u, const uint32_t *v, int64_t n_pairs, const char *column_name,
+                            cleora_graph_t **out);
+/* Adopt a prebuilt CSR (copied).  `n_rows` rows over `n_cols` columns; for a full graph n_rows == n_cols.  A
+ * row shard of a larger graph has n_rows < n_cols and `row_offset` = global index of its first row (used by
+ * the residual mix and by init).  `val_sym`, `row_sum`, `entity_hash` may be NULL. */
+int cleora_graph_from_csr(const int64_t *rowptr, const uint32_t *col, const float *val_left, const float *val_sym,
+                          const float *row_sum, const uint64_t *entity_hash, int64_t n_rows, int64_t n_cols,
+                          int64_t row_offset, cleora_graph_t **out);
+void cleora_graph_destroy(cleora_graph_t *g);
+/* Drop the cached device copy (CSR stays on the host). */
+int cleora_graph_release_device(cleora_graph_t *g);
+
+/* --- introspection (getters of the pyclass: src/sparse_matrix.rs:56-66, src/lib.rs:175-240,254-318) ------- */
+int64_t cleora_graph_num_entities(const cleora_graph_t *g); /* rows  (len(entity_ids)) */
+int64_t cleora_graph_num_cols(const cleora_graph_t *g);
+int64_t cleora_graph_num_edges(const cleora_graph_t *g);    /* nnz   (len(edges))      */
+int cleora_graph_copy_csr(const cleora_graph_t *g, int64_t *rowptr, uint32_t *col, float *val_left, float *val_sym);
+int cleora_graph_copy_row_sums(const cleora_graph_t *g, float *out);       /* entity_degrees */
+int cleora_graph_copy_entity_hashes(const cleora_graph_t *g, uint64_t *out);
+int cleora_graph_copy_column_ids(const cleora_graph_t *g, uint8_t *out);
+int64_t cleora_graph_entity_ids_nbytes(const cleora_graph_t *g);
+int cleora_graph_copy_entity_ids(const cleora_graph_t *g, char *buf, int64_t *offsets /* n+1 */);
+/* entity_ids setter (#[pyo3(get, set)], src/sparse_matrix.rs:60): re-hashes, because
+ * initialize_deterministically hashes the CURRENT ids (src/lib.rs:75). */
+int cleora_graph_set_entity_ids(cleora_graph_t *g, const char *buf, const int64_t *offsets, int64_t n);
+/* Restore the descriptor / column ids of an adopted CSR (used by __setstate__, src/lib.rs:470-475). */
+int cleora_graph_set_descriptor(cleora_graph_t *g, int col_a_id, const char *col_a_name, int col_b_id,
+                                const char *col_b_name);
+int cleora_graph_set_column_ids(cleora_graph_t *g, const uint8_t *ids, int64_t n);
+const char *cleora_graph_col_name(const cleora_graph_t *g, int which /* 0 = a, 1 = b */);
+int cleora_graph_col_id(const cleora_graph_t *g, int which);
+int64_t cleora_graph_find_entity(const cleora_graph_t *g, const char *id, int64_t id_len); /* -1 if absent */
+
+/* XXH64(seed 0) of an entity id -- src/entity.rs:109-114. */
+uint64_t cleora_hash_entity(const char *bytes, int64_t len);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Hot path, host buffers.  One call = one reference pymethod.
+ * ------------------------------------------------------------------------------------------------------- */
+/* initialize_deterministically (src/lib.rs:242-252): out[n, d]. */
+int cleora_initialize_deterministically(cleora_graph_t *g, int64_t d, int64_t seed, float *out);
+/* left_/symmetric_markov_propagate (src/lib.rs:86-102): x[x_rows, d] -> out[n, d];
+ * CLEORA_ERR_VALUE "Embedding matrix has {} rows but graph has {} entities" when x_rows != n_cols. */
+int cleora_markov_propagate(cleora_graph_t *g, const float *x, int64_t x_rows, int64_t d, int markov, float *out);
+/* l2_normalize (src/lib.rs:414-424). */
+int cleora_l2_normalize(const float *x, int64_t n, int64_t d, float *out);
+/* embed_fast (src/lib.rs:320-364) and embed_fast_convergence (:366-412): init + device-resident loop. */
+int cleora_embed_fast(cleora_graph_t *g, int64_t d, int64_t iters, int markov, int64_t seed,
+                      float residual_weight, float *out);
+int cleora_embed_fast_convergence(cleora_graph_t *g, int64_t d, int64_t max_iters, int markov, int64_t seed,
+                                  float residual_weight, float convergence_threshold, float *out,
+                                  int64_t *iters_done);
+/* whiten_embeddings (pycleora/__init__.py:130-164): x[n, d] -> out[n, n_components] (n_components <= 0: d). */
+int cleora_whiten_embeddings(const float *x, int64_t n, int64_t d, int64_t n_components, float *out);
+/* The loop body of embed() when it cannot take the Rust fast path (pycleora/__init__.py:97-125), kept on the
+ * device for all iterations: propagate -> residual -> normalise -> whiten -> rmse early stop.
+ * x0 == NULL: deterministic init from `seed`.  residual_weight is the Python float (double).
+ * `timings_ms` (optional, 8 doubles): h2d, init, spmm, stats, eigh, apply, rmse, d2h accumulated over the call. */
+int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64_t iters, int markov, int64_t seed,
+                 double residual_weight, double convergence_threshold, int normalization, int whiten,
+                 float *out, int64_t *iters_done, double *timings_ms);
+
+/* Symmetric eigensolver used by the whitening step: `a` is the d x d covariance (row-major, f64, symmetric);
+ * on return `w[d]` holds eigenvalues in ASCENDING order and `a` the eigenvectors as COLUMNS (a[i*d + k] =
+ * component i of eigenvector k) -- numpy.linalg.eigh's contract (pycleora/__init__.py:145).  Return 0 on
+ * success.  Default (NULL): cuSOLVER Dsyevd on the device.  The Python binding installs numpy's LAPACK eigh,
+ * which is what the reference itself calls. */
+typedef int (*cleora_eigh_fn)(double *a, double *w, int64_t d, void *user);
+void cleora_set_eigh(cleora_eigh_fn fn, void *user);
+
+/* Pinned host staging memory for callers that want async copies (bench e2e). */
+int cleora_host_alloc(size_t nbytes, void **out);
+void cleora_host_free(void *p);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Device-level building blocks (row-sharded multi-GPU composition; all pointers are DEVICE pointers on the
+ * current device, `stream` is a cudaStream_t).  They enqueue and return.
+ * ------------------------------------------------------------------------------------------------------- */
+/* Upload (once) and return device views of the graph's CSR. */
+int cleora_dev_graph_prepare(cleora_graph_t *g);
+/* K0: out[n, d] = init_value(hash[i], j, seed). */
+int cleora_dev_init(const uint64_t *hash, int64_t n, int64_t d, int64_t seed, float *out, void *stream);
+/* K1: out[r, :] = norm( alpha * sum_e val[e] * x[col[e], :] + rw * resid[r, :] ) for the graph's rows.
+ * `x` is the FULL [n_cols, d] matrix; `resid` is NULL or the [n_rows, d] block of the previous iterate.
+ * The un-normalised product is bit-identical to src/embedding.rs:52-86 (same f32 operation order). */
+int cleora_dev_spmm(cleora_graph_t *g, int markov, const float *x, int64_t d, float *out, const float *resid,
+                    float alpha, float rw, int normalization, void *stream);
+/* Row normalisation alone (l2_normalize and the postprocess of user-supplied matrices). */
+int cleora_dev_normalize(const float *x, int64_t n, int64_t d, int normalization, float *out, void *stream);
+/* K2a: sums[d] (f64) += column sums of x[n, d]  (deterministic two-stage reduction; `sums` is overwritten
+ * when accumulate == 0). */
+int cleora_dev_col_sums(const float *x, int64_t n, int64_t d, double *sums, int accumulate, void *stream);
+/* K2b: cov[d, d] (f64, unscaled) = sum_r (x_r - mean)(x_r - mean)^T with mean given in f64; overwritten. */
+int cleora_dev_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, void *stream);
+/* K3: out[n, dout] = (x[n, d] - mean_f32[d]) @ T[d, dout]  (f32). */
+int cleora_dev_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
+                            int64_t dout, float *out, void *stream);
+/* sum((a - b)^2) over n elements, f64 accumulation; result[0] overwritten.  f64_diff == 0: f32 difference and
+ * square (src/embedding.rs:173-174); != 0: f64 difference and square (pycleora/__init__.py:975-976). */
+int cleora_dev_sq_diff_sum(const float *a, const float *b, int64_t n, int f64_diff, double *result, void *stream);
+/* Host step of the whitening: cov (f64, already divided by n-1) -> T (f32 [d, dout]) via the installed eigh. */
+int cleora_whiten_transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T);
+/* Bytes of device scratch currently held by the calling thread's workspace (diagnostics). */
+int64_t cleora_dev_workspace_bytes(void);
+/* Number of kernel launches issued by this library since process start (bench's gpu_launches). */
+int64_t cleora_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLEORA_B200_H */
