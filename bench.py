@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- edges/sec through the 40-iteration embed() loop (BASELINE.json's metric).
+
+  python bench.py --gpus 1 --steps 2 --warmup 3                 # our arm, one B200
+  torchrun ... bench.py --gpus N --steps K --warmup W           # row-sharded over N B200s (one rank per GPU)
+  python bench.py --impl reference --gpus 1 --steps 2 --warmup 1  # the reference's CPU path (restated: oracle/)
+
+A "step" is one full pass of the hot path over the workload: init -> 40 x (SpMM -> L2 -> whiten).  Default
+workload = BASELINE.json configs[1]: Erdos-Renyi 1M nodes / 20M edges, d=256, iters=40.
+`value`  : E * iters / t with graph and state resident in HBM, timed with CUDA events on the library's stream.
+`e2e`    : the same metric through the public host-buffer API (cleora_b200.embed on host arrays): CSR upload
+           and result download inside the timed region.
+`roofline`: SpMM (K1) algorithmic bytes / its mean launch time (CUDA events inside the library, same timed
+           region) against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nodes, input edges, d, generator, rng seed)   -- SURVEY.md 8d
+    "er-1m-20m-d256": dict(n=1_000_000, e=20_000_000, d=256, kind="er", seed=1),
+    "products-2.4m-62m-d256": dict(n=2_449_029, e=61_859_140, d=256, kind="chunglu", seed=2, alpha=0.5),
+    "er-200k-4m-d256": dict(n=200_000, e=4_000_000, d=256, kind="er", seed=1),
+    "er-50k-1m-d128": dict(n=50_000, e=1_000_000, d=128, kind="er", seed=1),
+}
+
+
+def gen_pairs(w):
+    """Synthetic edge list (numpy PCG64 default_rng(seed)); u != v, duplicates allowed (they merge)."""
+    rs = np.random.default_rng(w["seed"])
+    n, e = w["n"], w["e"]
+    if w["kind"] == "er":
+        u = rs.integers(0, n, size=e, dtype=np.int64)
+        v = rs.integers(0, n, size=e, dtype=np.int64)
+    else:  # Chung-Lu: endpoints drawn with probability ~ (i + i0)^-alpha
+        i0 = 10.0
+        wts = (np.arange(n, dtype=np.float64) + i0) ** (-w["alpha"])
+        cdf = np.cumsum(wts)
+        cdf /= cdf[-1]
+        u = np.searchsorted(cdf, rs.random(e)).astype(np.int64)
+        v = np.searchsorted(cdf, rs.random(e)).astype(np.int64)
+        perm = rs.permutation(n)          # decouple node id from weight rank
+        u, v = perm[u], perm[v]
+    keep = u != v
+    return u[keep].astype(np.uint32), v[keep].astype(np.uint32)
+
+
+def spmm_bytes(n, nnz, d):
+    """B_spmm = nnz*(4+4+4d) + 8(n+1) + 4nd  (no-reuse gather model)."""
+    return nnz * (8 + 4 * d) + 8 * (n + 1) + 4 * n * d
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference (CPU) arm
+def cpu_loop(og, d, iters, whiten, threads):
+    """The reference's CPU path restated (oracle/): Rust SpMM order + numpy L2 + numpy whitening."""
+    import oracle
+    x = oracle.init_matrix(og.hashes, d, 0)
+    t0 = time.perf_counter()
+    if whiten:
+        for _ in range(iters):
+            x = oracle.whiten_embeddings(oracle.normalize(oracle.spmm(og, x), "l2"))
+    else:
+        x = oracle.embed_fast(og, d, iters, x0=x)
+    return time.perf_counter() - t0
+
+
+def oracle_graph_from(g):
+    import oracle
+    rowptr, col, left, sym = g._csr()
+    return oracle.OracleGraph(rowptr, col, left, sym, g.entity_degrees, g.entity_hashes(),
+                              np.zeros(g.num_entities, np.uint8), None)
+
+
+def run_reference(args, w, name):
+    """--impl reference: the reference's own CPU implementation of the path.  The Rust crate cannot be built
+    here (no cargo/rustc), so this is the oracle port: C/OpenMP restatement of src/embedding.rs + the
+    reference's numpy whitening, all host threads.  One step = `sample_iters` iterations of the full workload."""
+    import cleora_b200 as cb
+    import oracle
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    u, v = gen_pairs(w)
+    g = cb.SparseMatrix.from_edge_arrays(u, v)          # host-only: CSR construction (no GPU work)
+    og = oracle_graph_from(g)
+    oracle.lib()
+    sample_iters = args.cpu_iters
+    for _ in range(min(args.warmup, 1)):
+        cpu_loop(og, w["d"], 1, args.whiten, cores)
+    times = [cpu_loop(og, w["d"], sample_iters, args.whiten, cores) for _ in range(args.steps)]
+    t = sum(times) / len(times)
+    value = len(u) * sample_iters / t
+    line = {
+        "impl": "reference", "metric": "edges/sec through the 40-iteration embed() loop", "value": value,
+        "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "nodes": g.num_entities, "edges": int(len(u)), "nnz": g.num_edges, "d": w["d"],
+                   "iters": args.iters, "whiten": bool(args.whiten)},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_iters} of {args.iters} iterations of the full workload per step "
+                                   "(restated Rust/rayon SpMM+L2 in C/OpenMP + the reference's numpy whitening)"},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, w, name):
+    import torch
+    import cleora_b200 as cb
+    from cleora_b200 import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    L = _lib.lib()
+    _lib.check(L.cleora_set_device(local))
+    if world > 1:
+        from cleora_b200 import sharded
+        return sharded.bench(args, w, name, gen_pairs, spmm_bytes, measured_peaks, ClockSampler)
+
+    d, iters = w["d"], args.iters
+    u, v = gen_pairs(w)
+    g = cb.SparseMatrix.from_edge_arrays(u, v)
+    n, nnz, E = g.num_entities, g.num_edges, int(len(u))
+    norm = _lib.NORM_L2_NUMPY if args.whiten else _lib.NORM_L2_RUST
+    dev_out = torch.empty((n, d), dtype=torch.float32, device="cuda")     # result stays in HBM for `value`
+    timings = np.zeros(8)
+
+    def step_resident(t=None):
+        done = np.zeros(1, np.int64)
+        if args.whiten:
+            _lib.check(L.cleora_embed(g._handle(), None, d, iters, 0, 0, 0.0, 0.0, norm, 1, _lib.f32p(dev_out.data_ptr()),
+                                      done.ctypes.data_as(_lib.c_i64p),
+                                      None if t is None else t.ctypes.data_as(_lib.c_f64p)))
+        else:
+            _lib.check(L.cleora_embed(g._handle(), None, d, iters, 0, 0, 0.0, 0.0, norm, 0, _lib.f32p(dev_out.data_ptr()),
+                                      done.ctypes.data_as(_lib.c_i64p),
+                                      None if t is None else t.ctypes.data_as(_lib.c_f64p)))
+
+    _lib.check(L.cleora_dev_graph_prepare(g._handle()))                 # CSR resident before the timed region
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = L.cleora_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()                                                          # legacy default stream == library stream
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        step_resident(timings)
+    ev1.record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall
+    launches = L.cleora_kernel_launch_count() - launches0
+    clk = clocks.stop()
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    value = E * iters / (ms_step * 1e-3)
+
+    # ---- e2e: public host API, host buffers, CSR upload + result download inside the timed region
+    pinned = cb.pinned_empty((n, d), np.float32)
+    e2e_times = []
+    for i in range(1 + args.e2e_steps):
+        _lib.check(L.cleora_graph_release_device(g._handle()))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if args.whiten:
+            g.embed_device(d, iters, "left", norm, 0, None, 0.0, 0.0, True, out=pinned)
+        else:
+            g.embed_device(d, iters, "left", norm, 0, None, 0.0, 0.0, False, out=pinned)
+        torch.cuda.synchronize()
+        if i > 0:
+            e2e_times.append(time.perf_counter() - t0)
+    e2e_t = sum(e2e_times) / len(e2e_times)
+    h2d = 8 * (n + 1) + nnz * (4 + 4 + 4) + 8 * n                       # rowptr + col + left + sym + hashes
+    d2h = 4 * n * d
+
+    # ---- roofline of the dominant kernel (K1 SpMM+L2), live CUDA-event time from the same timed region
+    peak, peak_src = measured_peaks()
+    spmm_ms = timings[2] / (iters * args.steps)
+    b_spmm = spmm_bytes(n, nnz, d)
+    achieved = b_spmm / (spmm_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(name)
+
+    # ---- CPU baseline beside it: bounded sample of the same workload on the host cores
+    cpu = None
+    if not args.no_cpu_baseline:
+        import oracle
+        cores = os.cpu_count() or 1
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        og = oracle_graph_from(g)
+        cpu_loop(og, d, 1, args.whiten, cores)
+        tc = cpu_loop(og, d, args.cpu_iters, args.whiten, cores)
+        cpu = {"value": E * args.cpu_iters / tc, "unit": "edges/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_iters} of {iters} iterations of the full workload, restated Rust/rayon SpMM+L2 "
+                         "(C/OpenMP, oracle/) + the reference's numpy whitening"}
+
+    line = {
+        "metric": "edges/sec through the 40-iteration embed() loop", "value": value, "unit": "edges/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "nodes": n, "edges": E, "nnz": nnz, "d": d, "iters": iters,
+                   "whiten": bool(args.whiten), "eigh": os.environ.get("CLEORA_B200_EIGH", "numpy"),
+                   "l2_flush": "inputs (X 1.0 GB + CSR 0.33 GB per iteration) exceed the 126 MB L2"},
+        "nnz_per_s": nnz * iters / (ms_step * 1e-3),
+        "e2e": {"value": E * iters / e2e_t, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_t},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel (K1: SpMM + fused L2)", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": b_spmm, "ms_per_launch": spmm_ms},
+        "phase_ms_per_iter": {k: timings[i] / (iters * args.steps) for i, k in
+                              enumerate(["h2d", "init", "spmm", "stats", "eigh", "apply", "rmse", "d2h"])},
+        "wall_ms_per_step": 1e3 * t_wall / args.steps,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="er-1m-20m-d256", choices=sorted(WORKLOADS))
+    ap.add_argument("--iters", type=int, default=40)
+    ap.add_argument("--whiten", type=int, default=1)
+    ap.add_argument("--cpu-iters", type=int, default=2, help="iterations per CPU sample (bounded baseline)")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w, args.workload)
+    else:
+        run_ours(args, w, args.workload)
+
+
+if __name__ == "__main__":
+    main()

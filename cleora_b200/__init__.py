@@ -16,13 +16,27 @@ from . import _lib
 from ._lib import check, ptr
 from .pycleora import SparseMatrix
 
-__all__ = ["SparseMatrix", "embed", "whiten_embeddings", "embed_using_baseline_cleora",
+__all__ = ["SparseMatrix", "embed", "whiten_embeddings", "embed_using_baseline_cleora", "pinned_empty",
            "DEFAULT_FEATURE_DIM", "DEFAULT_NUM_ITERATIONS"]
 
 DEFAULT_FEATURE_DIM = 256          # pycleora/__init__.py:12
 DEFAULT_NUM_ITERATIONS = 40        # pycleora/__init__.py:13
 
 _DEVICE_NORMS = {"l2": _lib.NORM_L2_NUMPY, "l1": _lib.NORM_L1_NUMPY, "none": _lib.NORM_NONE}
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """A numpy array over page-locked host memory (cudaMallocHost) for fast result downloads."""
+    import ctypes as C
+    import weakref
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    check(_lib.lib().cleora_host_alloc(max(nbytes, 1), C.byref(p)))
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, _lib.lib().cleora_host_free, p)
+    return arr
 
 
 def _validate_propagation(propagation: str) -> None:

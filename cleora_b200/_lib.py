@@ -134,3 +134,8 @@ def check(rc: int) -> None:
 
 def ptr(a: np.ndarray, ctype):
     return a.ctypes.data_as(ctype)
+
+
+def f32p(address: int):
+    """A raw address (e.g. torch.Tensor.data_ptr()) as float*."""
+    return C.cast(C.c_void_p(address), c_f32p)

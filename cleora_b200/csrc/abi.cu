@@ -602,7 +602,7 @@ extern "C" int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64
         float *cur = bx.p, *y = by.p, *w = bw.p;
         if (x0) {
             ph.begin();
-            CUDA_TRY(cudaMemcpyAsync(cur, x0, cnt * sizeof(float), cudaMemcpyHostToDevice, nullptr));
+            CUDA_TRY(cudaMemcpyAsync(cur, x0, cnt * sizeof(float), cudaMemcpyDefault, nullptr));   // host or device
             ph.end(PH_H2D);
         } else {
             if (!dg.hash && n) value_error("graph has no entity hashes");
@@ -642,7 +642,7 @@ extern "C" int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64
             if (stop) break;
         }
         ph.begin();
-        CUDA_TRY(cudaMemcpyAsync(out, result, cnt * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
+        CUDA_TRY(cudaMemcpyAsync(out, result, cnt * sizeof(float), cudaMemcpyDefault, nullptr));   // host or device
         ph.end(PH_D2H);
         CUDA_TRY(cudaStreamSynchronize(nullptr));
         ph.collect(timings_ms);

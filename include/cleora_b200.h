@@ -129,7 +129,8 @@ int cleora_embed_fast_convergence(cleora_graph_t *g, int64_t d, int64_t max_iter
 int cleora_whiten_embeddings(const float *x, int64_t n, int64_t d, int64_t n_components, float *out);
 /* The loop body of embed() when it cannot take the Rust fast path (pycleora/__init__.py:97-125), kept on the
  * device for all iterations: propagate -> residual -> normalise -> whiten -> rmse early stop.
- * x0 == NULL: deterministic init from `seed`.  residual_weight is the Python float (double).
+ * x0 == NULL: deterministic init from `seed`.  residual_weight is the Python float (double).  `x0` and `out` may
+ * also be DEVICE pointers (the copies use cudaMemcpyDefault), which keeps the result in HBM.
  * `timings_ms` (optional, 8 doubles): h2d, init, spmm, stats, eigh, apply, rmse, d2h accumulated over the call. */
 int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64_t iters, int markov, int64_t seed,
                  double residual_weight, double convergence_threshold, int normalization, int whiten,

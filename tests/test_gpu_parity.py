@@ -1,0 +1,327 @@
+"""Parity of the CUDA path against the CPU oracle and the committed reference goldens.
+Everything here calls through the C ABI (via the ctypes SparseMatrix mirror) and needs a B200: `-m gpu`.
+
+Tolerances (stated per test):
+  * integer / index / init / un-normalised SpMM: bit-exact;
+  * L2-normalised iterates, whiten=False, 40 iterations: <= 1e-5 relative per element (elements above 1% of the
+    matrix rms) and <= 1e-5 of the matrix scale everywhere;
+  * whitening stages teacher-forced: mean/cov <= 1e-12 relative (f64), apply-T <= 1e-5 of scale;
+  * whitened loop end to end: raw per-element where the spectrum is well separated, otherwise after orthogonal
+    Procrustes alignment and through the Gram matrix (the PCA eigenbasis is ill-conditioned, SURVEY.md finding 3).
+"""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+import cleora_b200 as cb
+import oracle
+from cleora_b200 import _lib
+from tests.helpers import KARATE_COLUMNS, KARATE_EDGES, er_lines, hyper_lines, scale_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(lines, columns, trim=16):
+    return cb.SparseMatrix.from_iterator(lines, columns, hyperedge_trim_n=trim), oracle.build_graph(lines, columns, trim)
+
+
+@pytest.fixture(scope="module")
+def er_pair():
+    return _pair(er_lines(20000, 200000, 7), "complex::reflexive::node")
+
+
+@pytest.fixture(scope="module")
+def skew_pair():
+    """Power-law-ish hypergraph with a few very long rows (long-row path) and many short ones."""
+    rs = np.random.default_rng(17)
+    w = 1.0 / np.arange(1, 6001) ** 0.9
+    w /= w.sum()
+    lines = []
+    for _ in range(30000):
+        k = int(rs.integers(2, 9))
+        lines.append(" ".join(str(int(t)) for t in rs.choice(6000, size=k, p=w)))
+    return _pair(lines, "complex::reflexive::n")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+# ------------------------------------------------------------------------------------------------ P1: init
+@pytest.mark.parametrize("d,seed", [(1, 0), (7, 3), (32, 0), (256, -5), (300, 2**40 + 1)])
+def test_init_bit_exact(er_pair, d, seed):
+    g, o = er_pair
+    np.testing.assert_array_equal(bits(g.initialize_deterministically(d, seed)), bits(oracle.init_matrix(o.hashes, d, seed)))
+
+
+# ------------------------------------------------------------------------------------------------ P2: snapshots
+@pytest.mark.parametrize("tag,markov,key", [("01", "left", "left_01"), ("02", "left", "left_02"),
+                                            ("01", "symmetric", "sym_01"), ("02", "symmetric", "sym_02")])
+def test_reference_snapshots_on_gpu(golden_dir, tag, markov, key):
+    """tests/snapshot.rs:18-50 through the CUDA SpMM: all 3200 integers of each insta snapshot."""
+    z = np.load(os.path.join(golden_dir, "snapshots.npz"))
+    g = cb.SparseMatrix.from_iterator([str(s) for s in z[f"lines_{tag}"]], str(z[f"columns_{tag}"]))
+    fn = g.left_markov_propagate if markov == "left" else g.symmetric_markov_propagate
+    got = (fn(z[f"emb_{tag}"]) * np.float32(1000.0)).astype(np.int32)
+    np.testing.assert_array_equal(got, z[key])
+
+
+# ------------------------------------------------------------------------------------------------ SpMM bit-exact
+@pytest.mark.parametrize("d", [1, 3, 8, 16, 32, 64, 96, 100, 128, 192, 256, 260, 384, 512, 1024])
+@pytest.mark.parametrize("markov", ["left", "symmetric"])
+def test_spmm_bit_exact_all_widths(er_pair, d, markov):
+    g, o = er_pair
+    x = np.random.default_rng(d).standard_normal((o.n, d)).astype(np.float32)
+    fn = g.left_markov_propagate if markov == "left" else g.symmetric_markov_propagate
+    np.testing.assert_array_equal(bits(fn(x)), bits(oracle.spmm(o, x, markov)))
+
+
+@pytest.mark.parametrize("d", [32, 128, 256])
+def test_spmm_bit_exact_skewed_rows(skew_pair, d):
+    g, o = skew_pair
+    assert np.diff(o.rowptr).max() > 2000
+    x = np.random.default_rng(1).standard_normal((o.n, d)).astype(np.float32)
+    np.testing.assert_array_equal(bits(g.left_markov_propagate(x)), bits(oracle.spmm(o, x, "left")))
+
+
+def test_spmm_edge_cases():
+    # single entity, self loop only; empty graph; d = 0
+    g, o = _pair(["a"], "complex::reflexive::n")
+    x = np.float32([[1.5, -2.0, 0.25]])
+    np.testing.assert_array_equal(g.left_markov_propagate(x), oracle.spmm(o, x))
+    e = cb.SparseMatrix()
+    assert e.left_markov_propagate(np.zeros((0, 4), np.float32)).shape == (0, 4)
+    g2, o2 = _pair(KARATE_EDGES, KARATE_COLUMNS)
+    assert g2.left_markov_propagate(np.zeros((34, 0), np.float32)).shape == (34, 0)
+    # non-contiguous input is copied, not rejected
+    xx = np.random.default_rng(0).standard_normal((34, 16)).astype(np.float32)
+    np.testing.assert_array_equal(g2.left_markov_propagate(xx[:, ::2]), oracle.spmm(o2, np.ascontiguousarray(xx[:, ::2])))
+
+
+# ------------------------------------------------------------------------------------------------ L2
+@pytest.mark.parametrize("d", [5, 32, 256, 300])
+def test_l2_normalize(er_pair, d):
+    g, _ = er_pair
+    x = np.random.default_rng(d).standard_normal((999, d)).astype(np.float32)
+    x[7] = 0.0                                                       # max(norm, 1e-10) guard
+    got, ref = g.l2_normalize(x), oracle.l2_normalize(x)
+    np.testing.assert_allclose(got, ref, rtol=1e-6, atol=0)          # tree vs sequential sum of squares
+    np.testing.assert_array_equal(got[7], 0.0)
+
+
+# ------------------------------------------------------------------------------------------------ P3: fast path
+def _assert_1e5(got, ref):
+    scale = float(np.sqrt(np.mean(ref.astype(np.float64) ** 2)))
+    assert scale_rel_err(got, ref) <= 1e-5
+    big = np.abs(ref) >= 1e-2 * scale
+    rel = np.abs(got.astype(np.float64) - ref)[big] / np.abs(ref[big])
+    assert rel.max() <= 1e-5, rel.max()
+
+
+@pytest.mark.parametrize("d,markov,rw", [(32, "left", 0.0), (256, "left", 0.0), (128, "symmetric", 0.0),
+                                         (64, "left", 0.3), (100, "left", 0.0), (256, "left", 1.5)])
+def test_embed_fast_40_iterations_within_1e5(er_pair, d, markov, rw):
+    """src/embedding.rs:106-136 x 40: fp32 within 1e-5 relative per element (north_star's bar)."""
+    g, o = er_pair
+    got = g.embed_fast(d, 40, propagation=markov, seed=3, residual_weight=rw)
+    ref = oracle.embed_fast(o, d, 40, markov, 3, rw)
+    _assert_1e5(got, ref)
+    np.testing.assert_allclose(np.linalg.norm(got.astype(np.float64), axis=1), 1.0, rtol=1e-5)
+
+
+def test_embed_fast_skewed_and_karate(skew_pair, golden_dir):
+    g, o = skew_pair
+    _assert_1e5(g.embed_fast(64, 40), oracle.embed_fast(o, 64, 40))
+    z = np.load(os.path.join(golden_dir, "embed_karate_d32_t40_now.npz"))
+    gk = cb.SparseMatrix.from_iterator([str(s) for s in z["lines"]], str(z["columns"]))
+    _assert_1e5(cb.embed(gk, 32, 40, whiten=False), z["out"])       # reference embed() output (whiten=False)
+
+
+def test_embed_fast_convergence(er_pair):
+    g, o = er_pair
+    for thr in (0.0, 5e-3, 1e-3):
+        got, it = g.embed_fast_convergence(32, 30, convergence_threshold=thr)
+        ref, it_ref = oracle.embed_fast_convergence(o, 32, 30, convergence_threshold=thr)
+        assert it == it_ref, (thr, it, it_ref)
+        _assert_1e5(got, ref)
+    assert cb.embed(g, 32, 30, whiten=False, convergence_threshold=5e-3).shape == (o.n, 32)
+
+
+# ------------------------------------------------------------------------------------------------ P4: whitening stages
+def _dev_stats(x):
+    """mean (f64) and unscaled centred Gram (f64) of a host matrix through the device-level ABI."""
+    import torch
+    L = _lib.lib()
+    n, d = x.shape
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    sums = torch.zeros(d, dtype=torch.float64, device="cuda")
+    cov = torch.zeros(d, d, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.cleora_dev_col_sums(xd.data_ptr(), n, d, sums.data_ptr(), 0, st))
+    mean = sums / n
+    _lib.check(L.cleora_dev_centered_gram(xd.data_ptr(), n, d, mean.data_ptr(), cov.data_ptr(), st))
+    torch.cuda.synchronize()
+    return mean.cpu().numpy(), cov.cpu().numpy()
+
+
+@pytest.mark.parametrize("n,d", [(3000, 48), (5000, 256), (777, 100), (20000, 512), (2, 8), (40, 64)])
+def test_mean_and_covariance_f64(n, d):
+    rs = np.random.default_rng(n + d)
+    x = oracle.normalize((rs.standard_normal((n, d)) * rs.uniform(0.2, 3.0, d) + rs.uniform(-1, 1, d)).astype(np.float32))
+    mean, gram = _dev_stats(x)
+    ref_mean, ref_cov = oracle.whiten_stats(x)
+    np.testing.assert_allclose(mean, ref_mean, rtol=1e-12, atol=1e-15)
+    cov = gram / (n - 1)
+    assert np.max(np.abs(cov - ref_cov)) <= 1e-12 * np.max(np.abs(ref_cov))
+    np.testing.assert_array_equal(cov, cov.T)
+
+
+@pytest.mark.parametrize("n,d,dout", [(3000, 48, 48), (5000, 256, 256), (777, 100, 100), (1000, 64, 10), (4097, 512, 512)])
+def test_apply_transform_given_identical_T(n, d, dout):
+    import torch
+    rs = np.random.default_rng(d)
+    x = oracle.normalize(rs.standard_normal((n, d)).astype(np.float32))
+    mean, cov = oracle.whiten_stats(x)
+    T = oracle.whiten_transform(cov, None if dout == d else dout)
+    ref = oracle.whiten_apply(x, mean, T)
+    L = _lib.lib()
+    xd = torch.from_numpy(x).cuda()
+    md = torch.from_numpy(mean.astype(np.float32)).cuda()
+    Td = torch.from_numpy(np.ascontiguousarray(T)).cuda()
+    out = torch.empty(n, dout, dtype=torch.float32, device="cuda")
+    _lib.check(L.cleora_dev_whiten_apply(xd.data_ptr(), n, d, md.data_ptr(), Td.data_ptr(), dout, out.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert scale_rel_err(out.cpu().numpy(), ref) <= 1e-5
+
+
+def test_whiten_embeddings_matches_reference_golden(golden_dir):
+    """Well-separated spectrum (column scales 0.5..3): PCA basis is well conditioned, compare per element."""
+    z = np.load(os.path.join(golden_dir, "whiten_stage.npz"))
+    got = cb.whiten_embeddings(z["normalized"])
+    ref = z["whitened"]
+    sign = np.sign(np.sum(got * ref, axis=0))                       # eigenvector sign is a LAPACK convention
+    assert scale_rel_err(got * sign, ref) <= 2e-4
+    gotk = cb.whiten_embeddings(z["normalized"], n_components=5)
+    assert gotk.shape == (3000, 5) and scale_rel_err(gotk * sign[:5], ref[:, :5]) <= 2e-4
+    one = np.float32([[1, 2, 3]])
+    np.testing.assert_array_equal(cb.whiten_embeddings(one), one)   # n <= 1: copy (pycleora/__init__.py:132-133)
+
+
+# ------------------------------------------------------------------------------------------------ P5: whitened loop
+def procrustes_err(a, b):
+    """|aQ - b| / |b| with Q = argmin over orthogonal matrices."""
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    u, _, vt = np.linalg.svd(a64.T @ b64)
+    return float(np.max(np.abs(a64 @ (u @ vt) - b64)) / np.max(np.abs(b64)))
+
+
+def gram_err(a, b, pairs=20000, seed=0):
+    rs = np.random.default_rng(seed)
+    i, j = rs.integers(0, a.shape[0], pairs), rs.integers(0, a.shape[0], pairs)
+    ga = np.einsum("ij,ij->i", a[i].astype(np.float64), a[j].astype(np.float64))
+    gb = np.einsum("ij,ij->i", b[i].astype(np.float64), b[j].astype(np.float64))
+    return float(np.max(np.abs(ga - gb)) / np.max(np.abs(gb)))
+
+
+@pytest.mark.parametrize("name,raw_tol", [("karate_d8_t5_w", 1e-4), ("karate_d32_t5_w", 2e-3), ("karate_d8_t40_w", 1e-4)])
+def test_default_embed_matches_reference_output_karate(golden_dir, name, raw_tol):
+    """pycleora.embed() default path (whiten=True) against the unmodified reference's output."""
+    z = np.load(os.path.join(golden_dir, f"embed_{name}.npz"))
+    kw = ast.literal_eval(str(z["kwargs"]))
+    g = cb.SparseMatrix.from_iterator([str(s) for s in z["lines"]], str(z["columns"]))
+    got = cb.embed(g, **kw)
+    ref = z["out"]
+    sign = np.sign(np.sum(got * ref, axis=0))
+    sign[sign == 0] = 1
+    assert scale_rel_err(got * sign, ref) <= raw_tol
+    assert gram_err(got, ref) <= 1e-4
+    # callback path reproduces the same iterates and hands out every one of them
+    seen = []
+    got_cb = cb.embed(g, callback=lambda i, e: seen.append((i, e.copy())), **kw)
+    assert [i for i, _ in seen] == list(range(kw["num_iterations"]))
+    np.testing.assert_array_equal(got_cb, seen[-1][1])
+    if "trace" in z.files:
+        assert gram_err(seen[0][1], z["trace"][0]) <= 1e-5
+
+
+def test_default_embed_er_graph_procrustes_and_gram(golden_dir):
+    """Near-degenerate covariance spectrum: raw element-wise agreement is not defined; the
+    subspace, the Gram matrix and the Procrustes-aligned iterate are."""
+    z = np.load(os.path.join(golden_dir, "embed_er2k_d32_t5_w.npz"))
+    g = cb.SparseMatrix.from_iterator([str(s) for s in z["lines"]], str(z["columns"]))
+    got, ref = cb.embed(g, 32, 5), z["out"]
+    assert procrustes_err(got, ref) <= 1e-4
+    assert gram_err(got, ref) <= 1e-5
+    c = np.cov(got.astype(np.float64), rowvar=False)
+    np.testing.assert_allclose(c, np.eye(32), atol=1e-4)             # whitened: unit covariance
+    np.testing.assert_allclose(got.astype(np.float64).mean(0), 0, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["karate_d16_t10_sym_res", "karate_d8_t30_conv", "karate_d16_t6_l1"])
+def test_embed_variants_against_reference(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, f"embed_{name}.npz"))
+    kw = ast.literal_eval(str(z["kwargs"]))
+    g = cb.SparseMatrix.from_iterator([str(s) for s in z["lines"]], str(z["columns"]))
+    got, ref = cb.embed(g, **kw), z["out"]
+    assert got.shape == ref.shape                                    # same early-stop iteration => same shape/basis
+    assert gram_err(got, ref) <= 1e-3
+    assert procrustes_err(got, ref) <= 5e-3
+
+
+def test_teacher_forced_iteration_on_er_graph(er_pair):
+    """One full default iteration from the ORACLE's iterate at t=3: SpMM+L2 <= 1e-6, then whitening compared
+    through Gram/Procrustes."""
+    g, o = er_pair
+    xt = oracle.embed(o, 64, 3)
+    y_ref = oracle.normalize(oracle.spmm(o, xt), "l2")
+    y, _ = g.embed_device(64, 1, "left", _lib.NORM_L2_NUMPY, 0, xt, 0.0, 0.0, False)
+    np.testing.assert_allclose(y, y_ref, rtol=1e-6, atol=1e-9)
+    z, _ = g.embed_device(64, 1, "left", _lib.NORM_L2_NUMPY, 0, xt, 0.0, 0.0, True)
+    z_ref = oracle.whiten_embeddings(y_ref)
+    assert gram_err(z, z_ref) <= 1e-5
+    assert procrustes_err(z, z_ref) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+@pytest.fixture(scope="module")
+def big_graph():
+    """200k nodes / 4M pairs, ER, integer ingest (no oracle at this size; size-independent properties instead)."""
+    rs = np.random.default_rng(1)
+    n, e = 200_000, 4_000_000
+    u, v = rs.integers(0, n, e), rs.integers(0, n, e)
+    k = u != v
+    return cb.SparseMatrix.from_edge_arrays(u[k], v[k])
+
+
+def test_full_size_properties(big_graph):
+    g = big_graph
+    n, d = g.num_entities, 256
+    ones = np.full((n, d), 0.5, np.float32)
+    out = g.left_markov_propagate(ones)
+    np.testing.assert_allclose(out, 0.5, rtol=2e-6)                  # rows of the left Markov operator sum to 1
+    rs = np.random.default_rng(2)
+    x, y = (rs.standard_normal((n, d)).astype(np.float32) for _ in range(2))
+    ax, ay, axy = g.left_markov_propagate(x), g.left_markov_propagate(y), g.left_markov_propagate(x + y)
+    assert scale_rel_err(axy, ax + ay) <= 1e-5                       # linearity
+    emb = g.embed_fast(d, 3)
+    np.testing.assert_allclose(np.linalg.norm(emb.astype(np.float64), axis=1), 1.0, rtol=1e-5)
+    # symmetric operator: <x, S y> == <S x, y>
+    sx, sy = g.symmetric_markov_propagate(x), g.symmetric_markov_propagate(y)
+    a, b = np.vdot(x.astype(np.float64), sy.astype(np.float64)), np.vdot(sx.astype(np.float64), y.astype(np.float64))
+    assert abs(a - b) <= 1e-6 * abs(a)
+    w = cb.embed(g, 128, 2)
+    w64 = w.astype(np.float64)
+    np.testing.assert_allclose(w64.mean(0), 0, atol=1e-5)
+    np.testing.assert_allclose(np.cov(w64, rowvar=False), np.eye(128), atol=2e-3)
+
+
+def test_launches_are_counted_and_timings_reported(er_pair):
+    g, _ = er_pair
+    before = _lib.lib().cleora_kernel_launch_count()
+    t = np.zeros(8)
+    g.embed_device(64, 3, timings=t)
+    assert _lib.lib().cleora_kernel_launch_count() - before >= 3 * 4
+    assert t[2] > 0 and t[3] > 0 and t[5] > 0
