@@ -213,7 +213,9 @@ def run_ours(args, w, name):
     ev0.record()                                                          # legacy default stream == library stream
     t_wall = time.perf_counter()
     for _ in range(args.steps):
-        step_resident(timings)
+        t_step = np.zeros(8)
+        step_resident(t_step)                  # the library reports per-call phase totals (CUDA events, stream 0)
+        timings += t_step
     ev1.record()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall

@@ -87,13 +87,29 @@ _lib = None
 _eigh_keepalive = None
 
 
+_blas_ctl = None
+
+
 def _numpy_eigh(a_ptr, w_ptr, d, _user):
     """numpy.linalg.eigh behind the C callback -- the very call the reference makes
-    (pycleora/__init__.py:145), so eigenvector signs/order follow the same LAPACK."""
+    (pycleora/__init__.py:145), so eigenvector signs/order follow the same LAPACK.  The d x d problem is far too
+    small for a 100+-thread BLAS pool (measured 55 ms at d=256 on a 128-thread host vs ~5 ms with 4 threads), so
+    the call runs under a thread limit (CLEORA_B200_EIGH_THREADS, default 4)."""
+    global _blas_ctl
     try:
         a = np.ctypeslib.as_array(a_ptr, shape=(d, d))
         w = np.ctypeslib.as_array(w_ptr, shape=(d,))
-        vals, vecs = np.linalg.eigh(a)
+        if _blas_ctl is None:
+            try:
+                from threadpoolctl import ThreadpoolController
+                _blas_ctl = ThreadpoolController()
+            except Exception:  # noqa: BLE001
+                _blas_ctl = False
+        if _blas_ctl:
+            with _blas_ctl.limit(limits=int(os.environ.get("CLEORA_B200_EIGH_THREADS", "4")), user_api="blas"):
+                vals, vecs = np.linalg.eigh(a)
+        else:
+            vals, vecs = np.linalg.eigh(a)
         a[:, :] = vecs
         w[:] = vals
         return 0
