@@ -333,11 +333,16 @@ void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool ac
 // cov = sum_r (x_r - mean)(x_r - mean)^T in IEEE f64 (the reference accumulates the covariance in f64,
 // pycleora/__init__.py:138-142; the PCA eigenbasis is sensitive to ~1/eigengap, so lower precision is not an
 // option).  FP64 tensor-core path: mma.sync m8n8k4 f64 (DMMA) -- tcgen05 has no f64 kind.
-// One CTA = one 64x64 block (bi <= bj) of the d x d matrix for one slice of rows; partial blocks are reduced in
-// slice order by gram_reduce (deterministic).
-static constexpr int GB = 64;     // block edge
-static constexpr int GK = 32;     // rows per staged chunk
-static constexpr int GLD = 68;    // smem leading dimension in doubles (68 mod 16 == 4: conflict-free fragments)
+// One CTA = one 128x128 block (bi <= bj) of the d x d matrix for one slice of rows, 16 warps each owning a 32x32
+// warp tile (4x4 DMMA fragments); in diagonal blocks the warp tiles strictly below the diagonal are skipped.
+// Rows are staged 16 at a time: 128-bit global loads -> centre in f64 -> smem (row stride 132 doubles, which makes
+// both the 32-byte staging stores and the m8n8k4 fragment loads bank-conflict free); the next chunk is prefetched
+// into registers while the current one feeds the tensor pipe.  Partial blocks are reduced in slice order by
+// gram_reduce_kernel (deterministic).
+static constexpr int GB = 128;    // block edge
+static constexpr int GK = 16;     // rows per staged chunk
+static constexpr int GLD = 132;   // smem leading dimension in doubles (132 mod 16 == 4)
+static constexpr int GT = 32;     // warp tile edge
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -345,13 +350,14 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256) gram_f64_kernel(const float *__restrict__ x, int64_t n, int d,
-                                                       const double *__restrict__ mean, double *__restrict__ partial,
-                                                       int nblk, int64_t rows_per_slice) {
-    __shared__ double As[GK][GLD];
-    __shared__ double Bs[GK][GLD];
-    // decode (bi, bj), bi <= bj, from the linear pair index
-    int bi = 0, rest = blockIdx.x;
+template <bool VEC4>
+__global__ void __launch_bounds__(512, 1) gram_f64_kernel(const float *__restrict__ x, int64_t n, int d,
+                                                          const double *__restrict__ mean, double *__restrict__ partial,
+                                                          int nblk, int64_t rows_per_slice) {
+    __shared__ __align__(16) double As[GK][GLD];
+    __shared__ __align__(16) double Bs[GK][GLD];
+    __shared__ double mean_a[GB], mean_b[GB];
+    int bi = 0, rest = blockIdx.x;                     // decode (bi, bj), bi <= bj, from the linear pair index
     while (rest >= nblk - bi) { rest -= nblk - bi; ++bi; }
     const int bj = bi + rest;
     const bool diag = bi == bj;
@@ -359,104 +365,122 @@ __global__ void __launch_bounds__(256) gram_f64_kernel(const float *__restrict__
     const int64_t r1 = min(n, r0 + rows_per_slice);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int wm = w >> 2, wn = w & 3;                 // warp tile: rows wm*32.., cols wn*16..
-    double acc[4][2][2];
+    const int wm = w >> 2, wn = w & 3;                 // warp tile: rows wm*32.., cols wn*32.. of the block
+    const bool active = !(diag && wm > wn);
+    if (tid < GB) {
+        mean_a[tid] = (bi * GB + tid < d) ? mean[bi * GB + tid] : 0.0;
+        mean_b[tid] = (bj * GB + tid < d) ? mean[bj * GB + tid] : 0.0;
+    }
+    double acc[4][4][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-    // staging map: thread -> (row lr + 16*i, 4 consecutive columns lc..lc+3) of the 32x64 chunk
-    const int lr = tid >> 4, lc = (tid & 15) * 4;
+    // staging map: thread -> (row tid/32, 4 consecutive columns (tid%32)*4 ..) of the 16 x 128 chunk
+    const int lr = tid >> 5, lc = (tid & 31) * 4;
     const int ca = bi * GB + lc, cb = bj * GB + lc;
-    double ma[4], mb[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        ma[q] = (ca + q < d) ? mean[ca + q] : 0.0;
-        mb[q] = (cb + q < d) ? mean[cb + q] : 0.0;
-    }
-    float ra[2][4], rb[2][4];
+    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
     auto fetch = [&](int64_t rbase) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int64_t r = rbase + lr + 16 * i;
+        const int64_t r = rbase + lr;
+        if (VEC4) {
+            ra = (r < r1 && ca < d) ? __ldg(reinterpret_cast<const float4 *>(x + r * d + ca)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!diag) rb = (r < r1 && cb < d) ? __ldg(reinterpret_cast<const float4 *>(x + r * d + cb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            float t[4], u[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                ra[i][q] = (r < r1 && ca + q < d) ? __ldg(x + r * d + ca + q) : 0.f;
-                if (!diag) rb[i][q] = (r < r1 && cb + q < d) ? __ldg(x + r * d + cb + q) : 0.f;
+                t[q] = (r < r1 && ca + q < d) ? __ldg(x + r * d + ca + q) : 0.f;
+                u[q] = (!diag && r < r1 && cb + q < d) ? __ldg(x + r * d + cb + q) : 0.f;
             }
+            ra = make_float4(t[0], t[1], t[2], t[3]);
+            rb = make_float4(u[0], u[1], u[2], u[3]);
         }
     };
     auto stage = [&](int64_t rbase) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int64_t r = rbase + lr + 16 * i;
-            const bool in = r < r1;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                As[lr + 16 * i][lc + q] = (in && ca + q < d) ? (double)ra[i][q] - ma[q] : 0.0;
-                if (!diag) Bs[lr + 16 * i][lc + q] = (in && cb + q < d) ? (double)rb[i][q] - mb[q] : 0.0;
-            }
+        const bool in = rbase + lr < r1;
+        // out-of-range rows / columns contribute exactly zero (x - mean is forced to 0, not to -mean)
+        double2 v0, v1;
+        v0.x = (in && ca + 0 < d) ? (double)ra.x - mean_a[lc + 0] : 0.0;
+        v0.y = (in && ca + 1 < d) ? (double)ra.y - mean_a[lc + 1] : 0.0;
+        v1.x = (in && ca + 2 < d) ? (double)ra.z - mean_a[lc + 2] : 0.0;
+        v1.y = (in && ca + 3 < d) ? (double)ra.w - mean_a[lc + 3] : 0.0;
+        *reinterpret_cast<double2 *>(&As[lr][lc]) = v0;
+        *reinterpret_cast<double2 *>(&As[lr][lc + 2]) = v1;
+        if (!diag) {
+            v0.x = (in && cb + 0 < d) ? (double)rb.x - mean_b[lc + 0] : 0.0;
+            v0.y = (in && cb + 1 < d) ? (double)rb.y - mean_b[lc + 1] : 0.0;
+            v1.x = (in && cb + 2 < d) ? (double)rb.z - mean_b[lc + 2] : 0.0;
+            v1.y = (in && cb + 3 < d) ? (double)rb.w - mean_b[lc + 3] : 0.0;
+            *reinterpret_cast<double2 *>(&Bs[lr][lc]) = v0;
+            *reinterpret_cast<double2 *>(&Bs[lr][lc + 2]) = v1;
         }
     };
 
     if (r0 < r1) fetch(r0);
     for (int64_t rb0 = r0; rb0 < r1; rb0 += GK) {
-        __syncthreads();                       // previous chunk fully consumed
+        __syncthreads();                       // previous chunk fully consumed (and mean_* visible on the first trip)
         stage(rb0);
         __syncthreads();
-        if (rb0 + GK < r1) fetch(rb0 + GK);    // prefetch next chunk into registers while computing
-        const double(*Bp)[GLD] = diag ? As : Bs;
+        if (rb0 + GK < r1) fetch(rb0 + GK);    // prefetch the next chunk into registers while computing
+        if (active) {
+            const double(*Bp)[GLD] = diag ? As : Bs;
 #pragma unroll
-        for (int kk = 0; kk < GK / 4; ++kk) {
-            const int kr = kk * 4 + (lane & 3);
-            double a[4], b[2];
+            for (int kk = 0; kk < GK / 4; ++kk) {
+                const int kr = kk * 4 + (lane & 3);
+                double a[4], b[4];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = As[kr][wm * 32 + mi * 8 + (lane >> 2)];
+                for (int mi = 0; mi < 4; ++mi) a[mi] = As[kr][wm * GT + mi * 8 + (lane >> 2)];
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni) b[ni] = Bp[kr][wn * 16 + ni * 8 + (lane >> 2)];
+                for (int ni = 0; ni < 4; ++ni) b[ni] = Bp[kr][wn * GT + ni * 8 + (lane >> 2)];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                    for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
         }
     }
+    if (!active) return;
     double *P = partial + (int64_t)blockIdx.y * d * d;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 2; ++ni)
+        for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int gr = bi * GB + wm * 32 + mi * 8 + (lane >> 2);
-                const int gc = bj * GB + wn * 16 + ni * 8 + (lane & 3) * 2 + j;
+                const int gr = bi * GB + wm * GT + mi * 8 + (lane >> 2);
+                const int gc = bj * GB + wn * GT + ni * 8 + (lane & 3) * 2 + j;
                 if (gr < d && gc < d) P[(int64_t)gr * d + gc] = acc[mi][ni][j];
             }
 }
 
-// cov[i][j] = cov[j][i] = sum over slices, for block-upper (i-block <= j-block) entries.
+// cov[i][j] = cov[j][i] = sum over slices, for the computed entries (32-tile of i <= 32-tile of j).
 __global__ void gram_reduce_kernel(const double *__restrict__ partial, int slices, int d, double *__restrict__ cov) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)d * d) return;
     const int i = (int)(idx / d), j = (int)(idx - (int64_t)i * d);
-    if (i / GB > j / GB) return;
+    if (i / GT > j / GT) return;
     double s = 0.0;
     for (int k = 0; k < slices; ++k) s += partial[(int64_t)k * d * d + idx];
     cov[idx] = s;
-    if (i / GB != j / GB) cov[(int64_t)j * d + i] = s;
+    if (i / GT != j / GT) cov[(int64_t)j * d + i] = s;
 }
 
 void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st) {
     if (d == 0) return;
     const int nblk = (int)((d + GB - 1) / GB);
     const int npairs = nblk * (nblk + 1) / 2;
-    int64_t slices = std::max<int64_t>(1, std::min<int64_t>((n + 4 * GK - 1) / (4 * GK), (148 * 6) / npairs));
+    // one resident CTA per SM: ~148 CTAs in flight, a few waves when n is large
+    int64_t slices = std::max<int64_t>(1, std::min<int64_t>((n + 8 * GK - 1) / (8 * GK), (148 * 2 + npairs - 1) / npairs));
     slices = std::min<int64_t>(slices, 65535);
     const int64_t rows_per_slice = std::max<int64_t>(GK, ((n + slices - 1) / slices + GK - 1) / GK * GK);
     slices = std::max<int64_t>(1, (n + rows_per_slice - 1) / rows_per_slice);
     double *partial = (double *)workspace().gram_partials.get(size_t(slices) * size_t(d) * size_t(d) * sizeof(double));
     dim3 grid((unsigned)npairs, (unsigned)slices);
-    gram_f64_kernel<<<grid, 256, 0, st>>>(x, n, (int)d, mean, partial, nblk, rows_per_slice);
+    if (d % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+        gram_f64_kernel<true><<<grid, 512, 0, st>>>(x, n, (int)d, mean, partial, nblk, rows_per_slice);
+    else
+        gram_f64_kernel<false><<<grid, 512, 0, st>>>(x, n, (int)d, mean, partial, nblk, rows_per_slice);
     LAUNCH_CHECK();
     const int64_t tot = d * d;
     gram_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(partial, (int)slices, (int)d, cov);
