@@ -270,7 +270,7 @@ def run_ours(args, w, name):
         "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "nodes": n, "edges": E, "nnz": nnz, "d": d, "iters": iters,
-                   "whiten": bool(args.whiten), "eigh": os.environ.get("CLEORA_B200_EIGH", "numpy"),
+                   "whiten": bool(args.whiten), "eigh": os.environ.get("CLEORA_B200_EIGH", "cusolver"),
                    "l2_flush": "inputs (X 1.0 GB + CSR 0.33 GB per iteration) exceed the 126 MB L2"},
         "nnz_per_s": nnz * iters / (ms_step * 1e-3),
         "e2e": {"value": E * iters / e2e_t, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -78,6 +78,7 @@ PROTOTYPES = {
     "cleora_dev_whiten_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_void_p, C.c_void_p]),
     "cleora_dev_sq_diff_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "cleora_dev_whiten_transform": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "cleora_whiten_transform_from_cov": (C.c_int, [c_f64p, C.c_int64, C.c_int64, c_f32p]),
     "cleora_dev_workspace_bytes": (C.c_int64, []),
     "cleora_kernel_launch_count": (C.c_int64, []),
@@ -131,7 +132,7 @@ def lib():
         fn = getattr(L, name)       # AttributeError here means header and library are out of sync
         fn.restype = res
         fn.argtypes = args
-    if os.environ.get("CLEORA_B200_EIGH", "numpy") == "numpy":
+    if os.environ.get("CLEORA_B200_EIGH", "cusolver") == "numpy":
         _eigh_keepalive = EIGH_FN(_numpy_eigh)
         L.cleora_set_eigh(_eigh_keepalive, None)
     _lib = L

@@ -205,11 +205,47 @@ void transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T) {
 }
 
 // Whitening of a device-resident matrix: Y[n,d] -> Z[n,dout].  Scratch: sums/cov (f64), mean32, T on device.
+// Device-resident eigensolver state: cuSOLVER Dsyevd on the caller's stream, workspace sized once per d.
+struct DeviceEigh {
+    cusolverDnHandle_t h = nullptr;
+    DevBuf<double> evec, eval, work;
+    DevBuf<int> info;
+    int64_t d = 0;
+    int lwork = 0;
+    void ensure(int64_t d_) {
+        if (!h && cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("cusolverDnCreate failed");
+        if (d == d_) return;
+        d = d_;
+        evec.alloc((size_t)d * d); eval.alloc((size_t)d); info.alloc(1);
+        if (cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)d, evec.p, (int)d, eval.p,
+                                        &lwork) != CUSOLVER_STATUS_SUCCESS)
+            throw std::runtime_error("cusolverDnDsyevd_bufferSize failed");
+        work.alloc((size_t)std::max(lwork, 1));
+    }
+    // cov (d x d, symmetric, device) -> T (d x dout f32, device); everything enqueued on `st`.
+    void transform(const double *cov, int64_t d_, int64_t dout, float *T, cudaStream_t st) {
+        ensure(d_);
+        if (cusolverDnSetStream(h, st) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("cusolverDnSetStream failed");
+        CUDA_TRY(cudaMemcpyAsync(evec.p, cov, sizeof(double) * d * d, cudaMemcpyDeviceToDevice, st));
+        if (cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)d, evec.p, (int)d, eval.p, work.p,
+                             lwork, info.p) != CUSOLVER_STATUS_SUCCESS)
+            throw std::runtime_error("cusolverDnDsyevd failed");
+        launch_build_transform(evec.p, eval.p, d, dout, T, st);
+    }
+    void check_info() {
+        int hinfo = 0;
+        if (info.p) CUDA_TRY(cudaMemcpy(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (hinfo != 0) throw std::runtime_error("cuSOLVER Dsyevd did not converge (info=" + std::to_string(hinfo) + ")");
+    }
+    ~DeviceEigh() { if (h) cusolverDnDestroy(h); }
+};
+
 struct WhitenState {
     DevBuf<double> sums, cov;
     DevBuf<float> mean32, T;
     std::vector<double> h_cov;
     std::vector<float> h_T;
+    DeviceEigh eig;
     int64_t d = 0, dout = 0;
     void ensure(int64_t d_, int64_t dout_) {
         if (d == d_ && dout == dout_) return;
@@ -261,12 +297,16 @@ void whiten_device(const float *Y, int64_t n, int64_t d, int64_t dout, float *Z,
     launch_centered_gram(Y, n, d, ws.sums.p, ws.cov.p, st);
     launch_scale_f64(ws.cov.p, d * d, 1.0 / (double)(n - 1), st);        // cov *= 1/(n-1)
     launch_f64_to_f32(ws.sums.p, ws.mean32.p, d, st);                    // mean.astype(float32)
-    CUDA_TRY(cudaMemcpyAsync(ws.h_cov.data(), ws.cov.p, sizeof(double) * d * d, cudaMemcpyDeviceToHost, st));
     ph.end(PH_STATS);
     ph.begin();
-    CUDA_TRY(cudaStreamSynchronize(st));
-    transform_from_cov(ws.h_cov.data(), d, dout, ws.h_T.data());
-    CUDA_TRY(cudaMemcpyAsync(ws.T.p, ws.h_T.data(), sizeof(float) * d * dout, cudaMemcpyHostToDevice, st));
+    if (g_eigh) {            // host eigensolver installed by the binding (e.g. numpy's LAPACK): one round trip
+        CUDA_TRY(cudaMemcpyAsync(ws.h_cov.data(), ws.cov.p, sizeof(double) * d * d, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        transform_from_cov(ws.h_cov.data(), d, dout, ws.h_T.data());
+        CUDA_TRY(cudaMemcpyAsync(ws.T.p, ws.h_T.data(), sizeof(float) * d * dout, cudaMemcpyHostToDevice, st));
+    } else {                 // default: cuSOLVER on the stream, no host synchronisation inside the loop
+        ws.eig.transform(ws.cov.p, d, dout, ws.T.p, st);
+    }
     ph.end(PH_EIGH);
     ph.begin();
     launch_whiten_apply(Y, n, d, ws.mean32.p, ws.T.p, dout, Z, st);
@@ -471,6 +511,24 @@ extern "C" int cleora_dev_sq_diff_sum(const float *a, const float *b, int64_t n,
                                       void *stream) {
     return guarded([&] { launch_sq_diff_sum(a, b, n, f64_diff != 0, result, (cudaStream_t)stream); });
 }
+extern "C" int cleora_dev_whiten_transform(const double *cov, int64_t d, int64_t dout, float *T, void *stream) {
+    return guarded([&] {
+        if (dout <= 0 || dout > d) value_error("n_components must be in [1, d]");
+        cudaStream_t st = (cudaStream_t)stream;
+        if (g_eigh) {
+            std::vector<double> h((size_t)d * d);
+            std::vector<float> hT((size_t)d * dout);
+            CUDA_TRY(cudaMemcpyAsync(h.data(), cov, sizeof(double) * d * d, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            transform_from_cov(h.data(), d, dout, hT.data());
+            CUDA_TRY(cudaMemcpyAsync(T, hT.data(), sizeof(float) * d * dout, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        } else {
+            static thread_local DeviceEigh eig;
+            eig.transform(cov, d, dout, T, st);
+        }
+    });
+}
 extern "C" int cleora_whiten_transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T) {
     return guarded([&] {
         if (dout <= 0 || dout > d) value_error("n_components must be in [1, d]");
@@ -576,6 +634,7 @@ extern "C" int cleora_whiten_embeddings(const float *x, int64_t n, int64_t d, in
         Phase ph;
         whiten_device(dx.p, n, d, dout, dz.p, ws, nullptr, ph);
         CUDA_TRY(cudaMemcpy(out, dz.p, dz.n * sizeof(float), cudaMemcpyDeviceToHost));
+        ws.eig.check_info();
     });
 }
 
@@ -645,6 +704,7 @@ extern "C" int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64
         CUDA_TRY(cudaMemcpyAsync(out, result, cnt * sizeof(float), cudaMemcpyDefault, nullptr));   // host or device
         ph.end(PH_D2H);
         CUDA_TRY(cudaStreamSynchronize(nullptr));
+        ws.eig.check_info();
         ph.collect(timings_ms);
         if (iters_done) *iters_done = done;
     });

@@ -67,6 +67,7 @@ void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *me
 void launch_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
                          float *out, cudaStream_t st);
 void launch_sq_diff_sum(const float *a, const float *b, int64_t n, bool f64_diff, double *result, cudaStream_t st);
+void launch_build_transform(const double *V, const double *w, int64_t d, int64_t dout, float *T, cudaStream_t st);
 void launch_scale_f64(double *v, int64_t n, double factor, cudaStream_t st);
 void launch_f64_to_f32(const double *in, float *out, int64_t n, cudaStream_t st);
 

@@ -305,13 +305,24 @@ __global__ void __launch_bounds__(256) col_sums_stage1(const float *__restrict__
         if (c0 + t * 32 + lane < d) partial[w * d + c0 + t * 32 + lane] = acc[t];
 }
 
-__global__ void col_sums_stage2(const double *__restrict__ partial, int64_t W, int d, double *__restrict__ sums,
-                                int accumulate) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= d) return;
+// blockDim = (32 columns, 8 parts): thread (c, p) adds the partials w = p, p+8, ... of its column (coalesced over c),
+// then the 8 parts are combined in fixed order -> deterministic.
+__global__ void __launch_bounds__(256) col_sums_stage2(const double *__restrict__ partial, int64_t W, int d,
+                                                       double *__restrict__ sums, int accumulate) {
+    __shared__ double sh[8][33];
+    const int c = threadIdx.x, p = threadIdx.y;
+    const int j = blockIdx.x * 32 + c;
     double s = 0.0;
-    for (int64_t w = 0; w < W; ++w) s += partial[w * d + j];
-    sums[j] = accumulate ? sums[j] + s : s;
+    if (j < d)
+        for (int64_t w = p; w < W; w += 8) s += partial[w * d + j];
+    sh[p][c] = s;
+    __syncthreads();
+    if (p == 0 && j < d) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += sh[q][c];
+        sums[j] = accumulate ? sums[j] + t : t;
+    }
 }
 
 void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool accumulate, cudaStream_t st) {
@@ -325,7 +336,7 @@ void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool ac
         col_sums_stage1<8><<<(unsigned)blocks, threads, 0, st>>>(x, n, (int)d, c0, partial);
         LAUNCH_CHECK();
     }
-    col_sums_stage2<<<(unsigned)((d + 127) / 128), 128, 0, st>>>(partial, W, (int)d, sums, accumulate ? 1 : 0);
+    col_sums_stage2<<<(unsigned)((d + 31) / 32), dim3(32, 8), 0, st>>>(partial, W, (int)d, sums, accumulate ? 1 : 0);
     LAUNCH_CHECK();
 }
 
@@ -605,6 +616,25 @@ void launch_sq_diff_sum(const float *a, const float *b, int64_t n, bool f64_diff
     sq_diff_stage1<<<blocks, 256, 0, st>>>(a, b, n, f64_diff ? 1 : 0, partial);
     LAUNCH_CHECK();
     sq_diff_stage2<<<1, 32, 0, st>>>(partial, blocks, result);
+    LAUNCH_CHECK();
+}
+
+// ================================================================================================ PCA transform
+// T[i, k] = V[i, d-1-k] / sqrt(max(w[d-1-k], 1e-10)) as f32 -- pycleora/__init__.py:147-156 (eigh returns ascending
+// eigenvalues; the reference re-orders descending).  V is column-major (cuSOLVER): V[i + c*d].
+__global__ void build_transform_kernel(const double *__restrict__ V, const double *__restrict__ w, int d, int dout,
+                                       float *__restrict__ T) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)d * dout) return;
+    const int i = (int)(idx / dout), k = (int)(idx - (int64_t)i * dout);
+    const int src = d - 1 - k;
+    const double scale = 1.0 / sqrt(fmax(w[src], 1e-10));
+    T[idx] = (float)(V[(int64_t)src * d + i] * scale);
+}
+void launch_build_transform(const double *V, const double *w, int64_t d, int64_t dout, float *T, cudaStream_t st) {
+    const int64_t tot = d * dout;
+    if (tot == 0) return;
+    build_transform_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(V, w, (int)d, (int)dout, T);
     LAUNCH_CHECK();
 }
 

@@ -135,12 +135,9 @@ class CudaBackend:
         check(self.L.cleora_dev_sq_diff_sum(a.data_ptr(), b.data_ptr(), count, 1 if f64 else 0, out.data_ptr(),
                                             self.stream()))
 
-    def transform_from_cov(self, cov_host: np.ndarray, d: int) -> np.ndarray:
-        T = np.empty((d, d), np.float32)
-        cov_host = np.ascontiguousarray(cov_host, np.float64)
-        check(self.L.cleora_whiten_transform_from_cov(cov_host.ctypes.data_as(_lib.c_f64p), d, d,
-                                                      T.ctypes.data_as(_lib.c_f32p)))
-        return T
+    def transform(self, cov, d: int, T) -> None:
+        """cov (device f64, scaled) -> T (device f32) on the current stream (cuSOLVER unless a host eigh is set)."""
+        check(self.L.cleora_dev_whiten_transform(cov.data_ptr(), d, d, T.data_ptr(), self.stream()))
 
     def sync(self):
         self.torch.cuda.synchronize()
@@ -223,9 +220,8 @@ class ShardedEmbedder:
                     timers.stop(t)
                 t = timers.start("eigh") if timers else None
                 if s.rank == 0:
-                    Th = be.transform_from_cov(self.cov.cpu().numpy(), d)
-                    self.T.copy_(be.from_numpy(Th))
-                dist.broadcast(self.T, src=0, group=self.group)
+                    be.transform(self.cov, d, self.T)
+                dist.broadcast(self.T, src=0, group=self.group)       # one eigensolve, identical T everywhere
                 if timers:
                     timers.stop(t)
                 t = timers.start("apply") if timers else None

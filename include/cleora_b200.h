@@ -139,8 +139,8 @@ int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64_t iters, i
 /* Symmetric eigensolver used by the whitening step: `a` is the d x d covariance (row-major, f64, symmetric);
  * on return `w[d]` holds eigenvalues in ASCENDING order and `a` the eigenvectors as COLUMNS (a[i*d + k] =
  * component i of eigenvector k) -- numpy.linalg.eigh's contract (pycleora/__init__.py:145).  Return 0 on
- * success.  Default (NULL): cuSOLVER Dsyevd on the device.  The Python binding installs numpy's LAPACK eigh,
- * which is what the reference itself calls. */
+ * success.  Default (NULL): cuSOLVER Dsyevd on the device, enqueued on the loop's stream (no host sync).  Set
+ * CLEORA_B200_EIGH=numpy to make the Python binding install numpy's LAPACK eigh, the call the reference makes. */
 typedef int (*cleora_eigh_fn)(double *a, double *w, int64_t d, void *user);
 void cleora_set_eigh(cleora_eigh_fn fn, void *user);
 
@@ -174,6 +174,10 @@ int cleora_dev_whiten_apply(const float *x, int64_t n, int64_t d, const float *m
 /* sum((a - b)^2) over n elements, f64 accumulation; result[0] overwritten.  f64_diff == 0: f32 difference and
  * square (src/embedding.rs:173-174); != 0: f64 difference and square (pycleora/__init__.py:975-976). */
 int cleora_dev_sq_diff_sum(const float *a, const float *b, int64_t n, int f64_diff, double *result, void *stream);
+/* cov (f64 [d, d], device, already divided by n-1) -> T (f32 [d, dout], device) on `stream`: cuSOLVER Dsyevd +
+ * a transform-building kernel, no host synchronisation -- unless a host eigensolver is installed
+ * (cleora_set_eigh), in which case the call makes one synchronous round trip. */
+int cleora_dev_whiten_transform(const double *cov, int64_t d, int64_t dout, float *T, void *stream);
 /* Host step of the whitening: cov (f64, already divided by n-1) -> T (f32 [d, dout]) via the installed eigh. */
 int cleora_whiten_transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T);
 /* Bytes of device scratch currently held by the calling thread's workspace (diagnostics). */

@@ -68,8 +68,8 @@ class OracleBackend:
             dl = aa - bb
             out.numpy()[0] = float(np.sum((dl * dl).astype(np.float64)))
 
-    def transform_from_cov(self, cov_host, d):
-        return oracle.whiten_transform(cov_host)
+    def transform(self, cov, d, T):
+        T.numpy()[:] = oracle.whiten_transform(cov.numpy())
 
     def sync(self):
         pass
