@@ -112,17 +112,23 @@ def embed(
     else:
         x0 = None
 
+    # The rmse early stop on the whitened path compares successive iterates element-wise, so it depends on the
+    # eigensolver's sign/ordering conventions; to stop at the reference's iteration the reference's own LAPACK eigh
+    # is used for such calls (otherwise: cuSOLVER on the device, no host round trip).
+    lapack = whiten and convergence_threshold > 0
     if callback is None:
-        out, _ = graph.embed_device(feature_dim, num_iterations, propagation, _DEVICE_NORMS[normalization], seed, x0,
-                                    residual_weight, convergence_threshold, whiten)
+        with _lib.host_eigh(lapack):
+            out, _ = graph.embed_device(feature_dim, num_iterations, propagation, _DEVICE_NORMS[normalization], seed,
+                                        x0, residual_weight, convergence_threshold, whiten)
         return out
 
     # per-iteration path: one device-resident iteration at a time so the callback sees every iterate
     embeddings = x0 if x0 is not None else graph.initialize_deterministically(feature_dim, seed)
     for i in range(num_iterations):
         prev = embeddings
-        embeddings, _ = graph.embed_device(embeddings.shape[1], 1, propagation, _DEVICE_NORMS[normalization], seed,
-                                           embeddings, residual_weight, 0.0, whiten)
+        with _lib.host_eigh(lapack):
+            embeddings, _ = graph.embed_device(embeddings.shape[1], 1, propagation, _DEVICE_NORMS[normalization],
+                                               seed, embeddings, residual_weight, 0.0, whiten)
         callback(i, embeddings)
         if convergence_threshold > 0 and i > 0:
             diff = embeddings.astype(np.float64, copy=False) - prev.astype(np.float64, copy=False)

@@ -132,11 +132,28 @@ def lib():
         fn = getattr(L, name)       # AttributeError here means header and library are out of sync
         fn.restype = res
         fn.argtypes = args
+    _eigh_keepalive = EIGH_FN(_numpy_eigh)
     if os.environ.get("CLEORA_B200_EIGH", "cusolver") == "numpy":
-        _eigh_keepalive = EIGH_FN(_numpy_eigh)
         L.cleora_set_eigh(_eigh_keepalive, None)
     _lib = L
     return L
+
+
+class host_eigh:
+    """Context manager: route the whitening eigensolve through numpy's LAPACK (the reference's call) while active."""
+
+    def __init__(self, enable: bool = True):
+        self.enable = enable and os.environ.get("CLEORA_B200_EIGH", "cusolver") != "numpy"
+
+    def __enter__(self):
+        if self.enable:
+            lib().cleora_set_eigh(_eigh_keepalive, None)
+        return self
+
+    def __exit__(self, *exc):
+        if self.enable:
+            lib().cleora_set_eigh(C.cast(None, EIGH_FN), None)
+        return False
 
 
 def check(rc: int) -> None:

@@ -15,6 +15,8 @@
 #include "../../include/cleora_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 
 namespace cleora {
 
@@ -568,9 +570,23 @@ __global__ void __launch_bounds__(256) whiten_apply_kernel(const float *__restri
     }
 }
 
+bool whiten_apply_tc_supported(int64_t d, int64_t dout);
+void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
+                            float *out, int norm, cudaStream_t st);
+
+static bool use_tensor_core_apply() {
+    static const bool on = [] { const char *e = getenv("CLEORA_B200_APPLY"); return !(e && std::string(e) == "simt"); }();
+    return on;
+}
+
 void launch_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
                          float *out, cudaStream_t st) {
     if (n == 0 || dout == 0) return;
+    if (use_tensor_core_apply() && whiten_apply_tc_supported(d, dout) &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mean_f32)) & 15) == 0) {
+        launch_whiten_apply_tc(x, n, d, mean_f32, T, dout, out, CLEORA_NORM_NONE, st);    // tcgen05 / TMEM path
+        return;
+    }
     dim3 grid((unsigned)((n + AM - 1) / AM), (unsigned)((dout + AN - 1) / AN));
     whiten_apply_kernel<<<grid, 256, 0, st>>>(x, n, (int)d, mean_f32, T, (int)dout, out);
     LAUNCH_CHECK();

@@ -1,0 +1,318 @@
+// K3 on the 5th-generation tensor cores:  out[n, N] = rownorm?( (x - mean_f32) @ T )   (pycleora/__init__.py:157-163)
+//
+// tcgen05.mma kind::tf32 with the accumulator in TMEM, "3xTF32" error compensation so the result keeps fp32-class
+// accuracy (each f32 operand is split a = a_hi + a_lo with a_hi = the top 19 bits; D = A_lo*B_hi + A_hi*B_lo +
+// A_hi*B_hi accumulated in fp32): the reference multiplies in f32 (np.dot), plain TF32 (10-bit mantissa) would
+// miss its 1e-5 bar.
+//
+// Shape: one CTA = 128 rows of x (UMMA M = 128), all N <= 256 output columns (UMMA N = N), K = d in chunks of 32.
+// Warp roles (320 threads, persistent over row tiles):
+//   warps 0-3  A producers: thread = row; 128-bit loads of 32 floats, centre, split hi/lo, 16-byte stores into the
+//              canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices, LBO 128 B, SBO 1024 B);
+//   warps 4-7  epilogue: tcgen05.ld of the warp's 32 TMEM lanes (thread = row), optional row L2 norm, global stores;
+//   warp  8    MMA issuer (one elected lane): 3 x 4 tcgen05.mma per K chunk, tcgen05.commit to free smem stages and to
+//              publish the accumulator;
+//   warp  9    B loader: the transform, pre-split and pre-tiled in global memory by prep_transform_kernel, is copied
+//              chunk by chunk with cp.async.bulk (TMA 1-D) signalling an mbarrier.
+// TMEM holds two accumulator buffers (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "device.cuh"
+#include "../../include/cleora_b200.h"
+
+#include <algorithm>
+
+namespace cleora {
+
+namespace tc {
+
+constexpr int BM = 128;            // rows per tile (UMMA M)
+constexpr int BK = 32;             // K per stage (floats) = 128 bytes per row
+constexpr int STAGES = 2;
+constexpr int NMAX = 256;          // UMMA N limit
+constexpr int A_BYTES = BM * BK * 4;            // 16 KB (one of hi / lo)
+constexpr int THREADS = 320;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    const long long t0 = clock64();
+    do {
+        if (clock64() - t0 > 8000000000LL) __trap();      // watchdog (~4 s): a protocol bug must not hang the GPU
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (Blackwell): start address, leading (K-direction) and
+// stride (M/N-direction 8-row group) byte offsets, all in 16-byte units.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// Instruction descriptor for kind::tf32: D = f32, A = B = tf32, both K-major, M x N.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__float_as_uint(a) & 0xFFFFE000u); }
+
+}  // namespace tc
+
+// Pre-split and pre-tile the transform for the tensor-core kernel.  For every K chunk c (32 rows of T) the image
+// is exactly what the UMMA descriptor expects for a K-major B operand [N x 32]: element (n, k) of the chunk at
+// byte (n%8)*16 + (k%4)*4 + (k/4)*128 + (n/8)*1024.  Bt = [chunk][hi|lo][N*32 floats].
+__global__ void prep_transform_kernel(const float *__restrict__ T, int d, int dout, float *__restrict__ Bt) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)d * dout) return;
+    const int k = (int)(idx / dout), n = (int)(idx - (int64_t)k * dout);
+    const int c = k / tc::BK, kk = k % tc::BK;
+    const float v = T[idx];
+    const float hi = tc::tf32_hi(v);
+    const float lo = v - hi;
+    const int64_t chunk_floats = (int64_t)dout * tc::BK;
+    const int64_t off = (int64_t)(n % 8) * 4 + (kk % 4) + (int64_t)(kk / 4) * 32 + (int64_t)(n / 8) * 256;
+    float *base = Bt + (int64_t)c * 2 * chunk_floats;
+    base[off] = hi;
+    base[chunk_floats + off] = lo;
+}
+
+template <int NORM>   // 0: none, 2: row L2 (x / max(norm, 1e-10)) fused into the epilogue
+__global__ void __launch_bounds__(tc::THREADS, 1)
+whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const float *__restrict__ mean,
+                       const float *__restrict__ Bt, int N, float *__restrict__ out) {
+    using namespace tc;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int b_bytes = N * BK * 4;                                  // one of hi / lo
+    unsigned char *sA = smem_raw;                                    // STAGES x (A_hi, A_lo)
+    unsigned char *sB = sA + STAGES * 2 * A_BYTES;                   // STAGES x (B_hi, B_lo)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * 2 * b_bytes);
+    uint64_t *full_a = bars;                 // [STAGES] count 128
+    uint64_t *full_b = bars + STAGES;        // [STAGES] count 1 + tx
+    uint64_t *empty = bars + 2 * STAGES;     // [STAGES] count 1 (tcgen05.commit)
+    uint64_t *acc_full = bars + 3 * STAGES;  // [2] count 1 (tcgen05.commit)
+    uint64_t *acc_empty = acc_full + 2;      // [2] count 128
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = d / BK;
+    const int64_t n_tiles = (n + BM - 1) / BM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_a[s], 128); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {   // TMEM: 512 columns = two 256-column accumulator buffers
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------------ A producers (thread = row of the tile)
+        const int r = threadIdx.x;                     // 0..127
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t row = tile * BM + r;
+            const bool in = row < n;
+            const float4 *xr = reinterpret_cast<const float4 *>(x + (in ? row : 0) * (int64_t)d);
+            for (int c = 0; c < n_chunks; ++c, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                float4 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = in ? __ldg(xr + c * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 *mp = reinterpret_cast<const float4 *>(mean + c * BK);
+                mbar_wait(&empty[s], ph ^ 1);          // stage free (first round passes immediately)
+                unsigned char *hi = sA + s * 2 * A_BYTES, *lo = hi + A_BYTES;
+                const int off = (r & 7) * 16 + (r >> 3) * 1024;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 m = __ldg(mp + q);
+                    float4 a, h, l;
+                    a.x = in ? __fsub_rn(v[q].x, m.x) : 0.f; a.y = in ? __fsub_rn(v[q].y, m.y) : 0.f;
+                    a.z = in ? __fsub_rn(v[q].z, m.z) : 0.f; a.w = in ? __fsub_rn(v[q].w, m.w) : 0.f;
+                    h.x = tf32_hi(a.x); h.y = tf32_hi(a.y); h.z = tf32_hi(a.z); h.w = tf32_hi(a.w);
+                    l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
+                    *reinterpret_cast<float4 *>(hi + off + q * 128) = h;
+                    *reinterpret_cast<float4 *>(lo + off + q * 128) = l;
+                }
+                fence_proxy_async();                   // generic-proxy smem writes -> visible to the tensor core
+                mbar_arrive(&full_a[s]);
+            }
+        }
+    } else if (warp < 8) {
+        // ------------------------------------------------------------------ epilogue (thread = row, own TMEM lane)
+        const int q4 = warp - 4;                       // TMEM lane quarter of this warp
+        const int r = q4 * 32 + lane;
+        uint32_t t = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            const int buf = t & 1;
+            mbar_wait(&acc_full[buf], (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NMAX);
+            const int64_t row = tile * BM + r;
+            float scale = 1.f;
+            uint32_t v[32];
+            if (NORM == CLEORA_NORM_L2_NUMPY) {
+                float ss = 0.f;
+                for (int c0 = 0; c0 < N; c0 += 32) {
+                    tmem_ld32(taddr + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { const float f = __uint_as_float(v[j]); ss = fmaf(f, f, ss); }
+                }
+                scale = fmaxf(sqrtf(ss), 1e-10f);
+            }
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                tmem_ld32(taddr + c0, v);
+                if (row < n) {
+                    float4 *op = reinterpret_cast<float4 *>(out + row * (int64_t)N + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o;
+                        o.x = __uint_as_float(v[4 * j + 0]); o.y = __uint_as_float(v[4 * j + 1]);
+                        o.z = __uint_as_float(v[4 * j + 2]); o.w = __uint_as_float(v[4 * j + 3]);
+                        if (NORM == CLEORA_NORM_L2_NUMPY) {
+                            o.x = __fdiv_rn(o.x, scale); o.y = __fdiv_rn(o.y, scale);
+                            o.z = __fdiv_rn(o.z, scale); o.w = __fdiv_rn(o.w, scale);
+                        }
+                        op[j] = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);              // accumulator buffer may be overwritten
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = make_idesc_tf32(BM, N);
+        uint32_t it = 0, t = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            const int buf = t & 1;
+            mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * NMAX);
+            for (int c = 0; c < n_chunks; ++c, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_a[s], ph);
+                mbar_wait(&full_b[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_u32(sA + s * 2 * A_BYTES), a_lo = a_hi + A_BYTES;
+                    const uint32_t b_hi = smem_u32(sB + s * 2 * b_bytes), b_lo = b_hi + b_bytes;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {                 // UMMA K = 8 tf32 = two 16-byte core columns
+                        const uint32_t ko = k * 256;
+                        const uint64_t dah = make_desc(a_hi + ko, 128, 1024), dal = make_desc(a_lo + ko, 128, 1024);
+                        const uint64_t dbh = make_desc(b_hi + ko, 128, 1024), dbl = make_desc(b_lo + ko, 128, 1024);
+                        mma_tf32(tmem_d, dal, dbh, idesc, (c | k) != 0);   // small terms first
+                        mma_tf32(tmem_d, dah, dbl, idesc, 1);
+                        mma_tf32(tmem_d, dah, dbh, idesc, 1);
+                    }
+                    mma_commit(&empty[s]);                             // stage reusable once these MMAs retire
+                    if (c == n_chunks - 1) mma_commit(&acc_full[buf]); // accumulator complete
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ B loader (TMA 1-D bulk copies)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int c = 0; c < n_chunks; ++c, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_b[s], 2 * b_bytes);
+                    bulk_g2s(sB + s * 2 * b_bytes, Bt + (int64_t)c * 2 * N * BK, 2 * b_bytes, &full_b[s]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+bool whiten_apply_tc_supported(int64_t d, int64_t dout) {
+    return d % tc::BK == 0 && d >= tc::BK && dout % 16 == 0 && dout >= 16 && dout <= tc::NMAX;
+}
+
+// Scratch for the pre-tiled transform lives in the caller's workspace (misc).
+void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
+                            float *out, int norm, cudaStream_t st) {
+    using namespace tc;
+    if (n == 0) return;
+    float *Bt = (float *)workspace().misc.get((size_t)2 * d * dout * sizeof(float));
+    const int64_t tot = d * dout;
+    prep_transform_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(T, (int)d, (int)dout, Bt);
+    LAUNCH_CHECK();
+    const int N = (int)dout;
+    const size_t smem = (size_t)STAGES * 2 * A_BYTES + (size_t)STAGES * 2 * N * BK * 4 + 16 * sizeof(uint64_t) + 16;
+    const int64_t n_tiles = (n + BM - 1) / BM;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
+    if (norm == CLEORA_NORM_L2_NUMPY) {
+        static bool attr = false;
+        if (!attr) { CUDA_TRY(cudaFuncSetAttribute(whiten_apply_tc_kernel<CLEORA_NORM_L2_NUMPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+        whiten_apply_tc_kernel<CLEORA_NORM_L2_NUMPY><<<grid, THREADS, smem, st>>>(x, n, (int)d, mean_f32, Bt, N, out);
+    } else {
+        static bool attr = false;
+        if (!attr) { CUDA_TRY(cudaFuncSetAttribute(whiten_apply_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+        whiten_apply_tc_kernel<0><<<grid, THREADS, smem, st>>>(x, n, (int)d, mean_f32, Bt, N, out);
+    }
+    LAUNCH_CHECK();
+}
+
+}  // namespace cleora
