@@ -271,6 +271,7 @@ def run_ours(args, w, name):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "nodes": n, "edges": E, "nnz": nnz, "d": d, "iters": iters,
                    "whiten": bool(args.whiten), "eigh": os.environ.get("CLEORA_B200_EIGH", "cusolver"),
+                   "pipeline_whiten": os.environ.get("CLEORA_B200_PIPELINE", "1") != "0",
                    "l2_flush": "inputs (X 1.0 GB + CSR 0.33 GB per iteration) exceed the 126 MB L2"},
         "nnz_per_s": nnz * iters / (ms_step * 1e-3),
         "e2e": {"value": E * iters / e2e_t, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -289,6 +290,10 @@ def run_ours(args, w, name):
 
 
 def main():
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the host-side CSR construction (rank 0 only) and the CPU
+    # baseline are OpenMP code, so give them the cores back (must happen before the libraries initialise OpenMP).
+    if os.environ.get("OMP_NUM_THREADS") == "1" and "WORLD_SIZE" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)

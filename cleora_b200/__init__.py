@@ -16,13 +16,19 @@ from . import _lib
 from ._lib import check, ptr
 from .pycleora import SparseMatrix
 
-__all__ = ["SparseMatrix", "embed", "whiten_embeddings", "embed_using_baseline_cleora", "pinned_empty",
+__all__ = ["SparseMatrix", "embed", "whiten_embeddings", "embed_using_baseline_cleora", "pinned_empty", "set_option",
            "DEFAULT_FEATURE_DIM", "DEFAULT_NUM_ITERATIONS"]
 
 DEFAULT_FEATURE_DIM = 256          # pycleora/__init__.py:12
 DEFAULT_NUM_ITERATIONS = 40        # pycleora/__init__.py:13
 
 _DEVICE_NORMS = {"l2": _lib.NORM_L2_NUMPY, "l1": _lib.NORM_L1_NUMPY, "none": _lib.NORM_NONE}
+
+
+def set_option(key: str, value: int) -> None:
+    """Library tuning switches (include/cleora_b200.h: cleora_set_option), e.g. ``set_option("pipeline_whiten", 0)``
+    keeps the reference's stage order exactly instead of overlapping the eigensolve with the next SpMM."""
+    check(_lib.lib().cleora_set_option(key.encode(), int(value)))
 
 
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "cleora_embed": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_double,
                                C.c_int, C.c_int, c_f32p, c_i64p, c_f64p]),
     "cleora_set_eigh": (None, [EIGH_FN, C.c_void_p]),
+    "cleora_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
     "cleora_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "cleora_host_free": (None, [C.c_void_p]),
     "cleora_dev_graph_prepare": (C.c_int, [C.c_void_p]),
@@ -135,6 +136,8 @@ def lib():
     _eigh_keepalive = EIGH_FN(_numpy_eigh)
     if os.environ.get("CLEORA_B200_EIGH", "cusolver") == "numpy":
         L.cleora_set_eigh(_eigh_keepalive, None)
+    if os.environ.get("CLEORA_B200_PIPELINE", "1") == "0":
+        L.cleora_set_option(b"pipeline_whiten", 0)
     _lib = L
     return L
 

@@ -102,7 +102,7 @@ struct DevBuf {
 void free_device_graph(DeviceGraph *dg) {
     if (!dg) return;
     cudaFree(dg->rowptr); cudaFree(dg->col); cudaFree(dg->left); cudaFree(dg->sym); cudaFree(dg->hash);
-    cudaFree(dg->long_rows);
+    cudaFree(dg->long_rows); cudaFree(dg->rsum_left); cudaFree(dg->rsum_sym);
     delete dg;
 }
 
@@ -261,16 +261,18 @@ struct Phase {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[8];
     cudaStream_t st = nullptr;
     cudaEvent_t a = nullptr;
-    void begin() {
+    void begin() { begin_on(st); }
+    void end(int which) { end_on(which, st); }
+    void begin_on(cudaStream_t s) {
         if (!on) return;
         cudaEventCreate(&a);
-        cudaEventRecord(a, st);
+        cudaEventRecord(a, s);
     }
-    void end(int which) {
+    void end_on(int which, cudaStream_t s) {
         if (!on) return;
         cudaEvent_t b;
         cudaEventCreate(&b);
-        cudaEventRecord(b, st);
+        cudaEventRecord(b, s);
         ev[which].push_back({a, b});
     }
     void collect(double *out) {
@@ -313,6 +315,98 @@ void whiten_device(const float *Y, int64_t n, int64_t d, int64_t dout, float *Z,
     ph.end(PH_APPLY);
 }
 
+// ---- options -------------------------------------------------------------------------------------------------
+std::atomic<int> g_opt_pipeline{1};
+
+// mean / covariance of Y (device) into ws.sums (mean, f64), ws.mean32, ws.cov (scaled by 1/(n-1))
+void stats_device(const float *Y, int64_t n, int64_t d, WhitenState &ws, cudaStream_t st) {
+    launch_col_sums(Y, n, d, ws.sums.p, false, st);
+    launch_scale_f64(ws.sums.p, d, 1.0 / (double)n, st);
+    launch_centered_gram(Y, n, d, ws.sums.p, ws.cov.p, st);
+    launch_scale_f64(ws.cov.p, d * d, 1.0 / (double)(n - 1), st);
+    launch_f64_to_f32(ws.sums.p, ws.mean32.p, d, st);
+}
+
+const float *row_scale_of(DeviceGraph &dg, int markov) {
+    float *&slot = markov == CLEORA_MARKOV_LEFT ? dg.rsum_left : dg.rsum_sym;
+    if (!slot) {
+        CUDA_TRY(cudaMalloc((void **)&slot, sizeof(float) * (size_t)std::max<int64_t>(dg.n_rows, 1)));
+        launch_row_value_sums(dg.rowptr, values_of(dg, markov), dg.n_rows, slot, nullptr);
+    }
+    return slot;
+}
+
+// Default whitened loop with the eigensolve taken off the critical path.
+//
+// Faithful order per iteration:  Y = rownorm(A X);  (mu, C) = stats(Y);  T = eig(C);  X' = (Y - 1 mu^T) T.
+// The next product is linear in X':  A X' = (A Y - (A 1) mu^T) T, so W = A Y does not need T and runs on the main
+// stream while cuSOLVER works on a second stream; the tensor-core GEMM then applies T to (W - s mu^T), s = A 1, and
+// normalises rows in its epilogue.  Same mathematics, different f32 rounding points (a few ulp); the final iterate
+// is produced by the plain apply.  Used only where every stage has a kernel for it (see eligible()).
+struct SecondStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t stats_done = nullptr, t_ready = nullptr;
+    SecondStream() {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&stats_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&t_ready, cudaEventDisableTiming));
+    }
+    ~SecondStream() {
+        if (stats_done) cudaEventDestroy(stats_done);
+        if (t_ready) cudaEventDestroy(t_ready);
+        if (s) cudaStreamDestroy(s);
+    }
+};
+
+bool pipeline_eligible(int64_t n, int64_t d, int64_t iters, int normalization, int whiten, double residual_weight,
+                       double convergence_threshold) {
+    return g_opt_pipeline.load() && g_eigh == nullptr && whiten && n > 1 && iters >= 2 &&
+           normalization == CLEORA_NORM_L2_NUMPY && residual_weight == 0.0 && convergence_threshold <= 0.0 &&
+           whiten_apply_tc_supported(d, d);
+}
+
+void embed_pipelined(DeviceGraph &dg, const float *val, int markov, float *cur, float *y, float *w, float *y2, int64_t n,
+                     int64_t d, int64_t iters, WhitenState &ws, Phase &ph, float **result) {
+    cudaStream_t A = nullptr;
+    SecondStream B;
+    ws.ensure(d, d);
+    const float *rowscale = row_scale_of(dg, markov);
+    ph.begin();
+    launch_spmm(dg, val, cur, d, y, nullptr, 1.f, 0.f, CLEORA_NORM_L2_NUMPY, A);
+    ph.end(PH_SPMM);
+    ph.begin();
+    stats_device(y, n, d, ws, A);
+    ph.end(PH_STATS);
+    for (int64_t it = 1; it < iters; ++it) {
+        CUDA_TRY(cudaEventRecord(B.stats_done, A));
+        CUDA_TRY(cudaStreamWaitEvent(B.s, B.stats_done, 0));
+        ph.begin_on(B.s);
+        ws.eig.transform(ws.cov.p, d, d, ws.T.p, B.s);                   // eigensolve || SpMM
+        ph.end_on(PH_EIGH, B.s);
+        CUDA_TRY(cudaEventRecord(B.t_ready, B.s));
+        ph.begin();
+        launch_spmm(dg, val, y, d, w, nullptr, 1.f, 0.f, CLEORA_NORM_NONE, A);      // W = A Y
+        ph.end(PH_SPMM);
+        CUDA_TRY(cudaStreamWaitEvent(A, B.t_ready, 0));
+        ph.begin();
+        launch_whiten_apply_tc(w, n, d, ws.mean32.p, ws.T.p, d, y2, CLEORA_NORM_L2_NUMPY, rowscale, A);
+        ph.end(PH_APPLY);
+        ph.begin();
+        stats_device(y2, n, d, ws, A);
+        ph.end(PH_STATS);
+        std::swap(y, y2);
+    }
+    ph.begin();
+    ws.eig.transform(ws.cov.p, d, d, ws.T.p, A);
+    ph.end(PH_EIGH);
+    ph.begin();
+    launch_whiten_apply(y, n, d, ws.mean32.p, ws.T.p, d, cur, A);          // X_T = (Y - 1 mu^T) T
+    ph.end(PH_APPLY);
+    CUDA_TRY(cudaStreamSynchronize(A));
+    CUDA_TRY(cudaStreamSynchronize(B.s));
+    *result = cur;
+}
+
 }  // namespace
 }  // namespace cleora
 
@@ -331,6 +425,13 @@ extern "C" int cleora_set_device(int device) {
 }
 extern "C" uint64_t cleora_hash_entity(const char *bytes, int64_t len) { return xxh64(bytes, (size_t)len, 0); }
 extern "C" void cleora_set_eigh(cleora_eigh_fn fn, void *user) { g_eigh = fn; g_eigh_user = user; }
+extern "C" int cleora_set_option(const char *key, int64_t value) {
+    return guarded([&] {
+        const std::string k = key ? key : "";
+        if (k == "pipeline_whiten") g_opt_pipeline.store(value != 0);
+        else value_error("unknown option '" + k + "'");
+    });
+}
 extern "C" int cleora_host_alloc(size_t nbytes, void **out) {
     return guarded([&] { require_device(); CUDA_TRY(cudaMallocHost(out, nbytes ? nbytes : 1)); });
 }
@@ -674,7 +775,14 @@ extern "C" int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64
         WhitenState ws;
         int64_t done = 0;
         float *result = cur;
-        for (int64_t it = 0; it < iters; ++it) {
+        const bool pipelined = pipeline_eligible(n, d, iters, normalization, whiten, residual_weight, convergence_threshold);
+        DevBuf<float> bw2, by2;
+        if (pipelined) {
+            bw2.alloc(cnt); by2.alloc(cnt);
+            embed_pipelined(dg, val, markov, cur, y, bw2.p, by2.p, n, d, iters, ws, ph, &result);
+            done = iters;
+        }
+        for (int64_t it = 0; it < (pipelined ? 0 : iters); ++it) {
             ph.begin();
             launch_spmm(dg, val, cur, d, y, use_res ? cur : nullptr, alpha, rwf, normalization, nullptr);
             ph.end(PH_SPMM);

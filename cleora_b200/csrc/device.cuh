@@ -20,6 +20,7 @@ struct DeviceGraph {
     // long-row schedule (rows with more than LONG_ROW_EDGES edges are split across warps)
     int64_t n_long = 0;
     int32_t *long_rows = nullptr;
+    float *rsum_left = nullptr, *rsum_sym = nullptr;   // A*1 per Markov type, built on first pipelined use
 };
 
 void set_error(const std::string &msg);
@@ -66,6 +67,10 @@ void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool ac
 void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st);
 void launch_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
                          float *out, cudaStream_t st);
+bool whiten_apply_tc_supported(int64_t d, int64_t dout);
+void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
+                            float *out, int norm, const float *rowscale, cudaStream_t st);
+void launch_row_value_sums(const int64_t *rowptr, const float *val, int64_t n, float *out, cudaStream_t st);
 void launch_sq_diff_sum(const float *a, const float *b, int64_t n, bool f64_diff, double *result, cudaStream_t st);
 void launch_build_transform(const double *V, const double *w, int64_t d, int64_t dout, float *T, cudaStream_t st);
 void launch_scale_f64(double *v, int64_t n, double factor, cudaStream_t st);

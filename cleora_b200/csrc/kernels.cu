@@ -467,6 +467,113 @@ __global__ void __launch_bounds__(512, 1) gram_f64_kernel(const float *__restric
             }
 }
 
+// v3: the same Gram with the staging taken off the critical path.  Raw f32 tiles are copied global -> shared with
+// cp.async (16-byte LDGSTS, 4 stages in flight, one __syncthreads per 16-row chunk); the f32 -> f64 conversion and
+// the centring happen when a fragment is loaded (each thread keeps the 8 means it needs in registers).  Numerics
+// are identical to gram_f64_kernel: (double)x - mean_f64, IEEE f64 DMMA accumulation in row order.
+static constexpr int G3_STAGES = 4;
+static constexpr int G3_LD = 136;          // floats per staged row (136 mod 32 == 8: conflict-free fragment loads)
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, int src_bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(512, 1) gram_f64_v3_kernel(const float *__restrict__ x, int64_t n, int d,
+                                                             const double *__restrict__ mean, double *__restrict__ partial,
+                                                             int nblk, int64_t rows_per_slice) {
+    extern __shared__ __align__(16) float g3_smem[];      // [G3_STAGES][2][GK][G3_LD]
+    int bi = 0, rest = blockIdx.x;
+    while (rest >= nblk - bi) { rest -= nblk - bi; ++bi; }
+    const int bj = bi + rest;
+    const bool diag = bi == bj;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice;
+    const int64_t r1 = min(n, r0 + rows_per_slice);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wm = w >> 2, wn = w & 3;
+    const bool active = !(diag && wm > wn);
+
+    double ma[4], mb[4];                                  // means of the 4+4 columns this lane's fragments touch
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ca = bi * GB + wm * GT + q * 8 + (lane >> 2), cb = bj * GB + wn * GT + q * 8 + (lane >> 2);
+        ma[q] = ca < d ? mean[ca] : 0.0;
+        mb[q] = cb < d ? mean[cb] : 0.0;
+    }
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    // copy map: thread -> (row tid/32, 16-byte column chunk tid%32) of the 16 x 128 tile, for both operands
+    const int lr = tid >> 5, lc = (tid & 31) * 4;
+    const int ca0 = bi * GB + lc, cb0 = bj * GB + lc;
+    const int64_t n_chunks = (r1 - r0 + GK - 1) / GK;
+    auto issue = [&](int64_t chunk) {
+        if (chunk < n_chunks) {
+            float *sa = g3_smem + (size_t)(chunk % G3_STAGES) * 2 * GK * G3_LD, *sb = sa + GK * G3_LD;
+            const int64_t r = r0 + chunk * GK + lr;
+            const bool rin = r < r1;
+            const float *ga = x + (rin ? r : 0) * (int64_t)d + (ca0 < d ? ca0 : 0);
+            cp_async16(sa + lr * G3_LD + lc, ga, (rin && ca0 < d) ? 16 : 0);          // zero-fill outside
+            if (!diag) {
+                const float *gb = x + (rin ? r : 0) * (int64_t)d + (cb0 < d ? cb0 : 0);
+                cp_async16(sb + lr * G3_LD + lc, gb, (rin && cb0 < d) ? 16 : 0);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < G3_STAGES - 1; ++s) issue(s);
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        cp_async_wait<G3_STAGES - 2>();                  // chunk c has landed (for this thread's copies)
+        __syncthreads();                                 // ... and for everyone's; chunk c-1 is fully consumed
+        issue(c + G3_STAGES - 1);                        // refill the stage consumed in the previous trip
+        if (active) {
+            const float *sa = g3_smem + (size_t)(c % G3_STAGES) * 2 * GK * G3_LD;
+            const float *sb = diag ? sa : sa + GK * G3_LD;
+            const int rows_valid = (int)min((int64_t)GK, r1 - (r0 + c * GK));
+#pragma unroll
+            for (int kk = 0; kk < GK / 4; ++kk) {
+                const int kr = kk * 4 + (lane & 3);
+                const bool kin = kr < rows_valid;        // rows past the slice end contribute exactly zero
+                double a[4], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    const float f = sa[kr * G3_LD + wm * GT + mi * 8 + (lane >> 2)];
+                    a[mi] = kin ? (double)f - ma[mi] : 0.0;
+                }
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const float f = sb[kr * G3_LD + wn * GT + ni * 8 + (lane >> 2)];
+                    b[ni] = kin ? (double)f - mb[ni] : 0.0;
+                }
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (!active) return;
+    double *P = partial + (int64_t)blockIdx.y * d * d;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int gr = bi * GB + wm * GT + mi * 8 + (lane >> 2);
+                const int gc = bj * GB + wn * GT + ni * 8 + (lane & 3) * 2 + j;
+                if (gr < d && gc < d) P[(int64_t)gr * d + gc] = acc[mi][ni][j];
+            }
+}
+
 // cov[i][j] = cov[j][i] = sum over slices, for the computed entries (32-tile of i <= 32-tile of j).
 __global__ void gram_reduce_kernel(const double *__restrict__ partial, int slices, int d, double *__restrict__ cov) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -490,7 +597,13 @@ void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *me
     slices = std::max<int64_t>(1, (n + rows_per_slice - 1) / rows_per_slice);
     double *partial = (double *)workspace().gram_partials.get(size_t(slices) * size_t(d) * size_t(d) * sizeof(double));
     dim3 grid((unsigned)npairs, (unsigned)slices);
-    if (d % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+    static const bool use_v3 = [] { const char *e = getenv("CLEORA_B200_GRAM"); return !(e && std::string(e) == "v2"); }();
+    if (use_v3 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const size_t smem = (size_t)G3_STAGES * 2 * GK * G3_LD * sizeof(float);      // 69,632 B
+        static bool attr = false;
+        if (!attr) { CUDA_TRY(cudaFuncSetAttribute(gram_f64_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        gram_f64_v3_kernel<<<grid, 512, smem, st>>>(x, n, (int)d, mean, partial, nblk, rows_per_slice);
+    } else if (d % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
         gram_f64_kernel<true><<<grid, 512, 0, st>>>(x, n, (int)d, mean, partial, nblk, rows_per_slice);
     else
         gram_f64_kernel<false><<<grid, 512, 0, st>>>(x, n, (int)d, mean, partial, nblk, rows_per_slice);
@@ -570,9 +683,6 @@ __global__ void __launch_bounds__(256) whiten_apply_kernel(const float *__restri
     }
 }
 
-bool whiten_apply_tc_supported(int64_t d, int64_t dout);
-void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
-                            float *out, int norm, cudaStream_t st);
 
 static bool use_tensor_core_apply() {
     static const bool on = [] { const char *e = getenv("CLEORA_B200_APPLY"); return !(e && std::string(e) == "simt"); }();
@@ -584,7 +694,7 @@ void launch_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean
     if (n == 0 || dout == 0) return;
     if (use_tensor_core_apply() && whiten_apply_tc_supported(d, dout) &&
         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mean_f32)) & 15) == 0) {
-        launch_whiten_apply_tc(x, n, d, mean_f32, T, dout, out, CLEORA_NORM_NONE, st);    // tcgen05 / TMEM path
+        launch_whiten_apply_tc(x, n, d, mean_f32, T, dout, out, CLEORA_NORM_NONE, nullptr, st);    // tcgen05 / TMEM path
         return;
     }
     dim3 grid((unsigned)((n + AM - 1) / AM), (unsigned)((dout + AN - 1) / AN));
@@ -651,6 +761,22 @@ void launch_build_transform(const double *V, const double *w, int64_t d, int64_t
     const int64_t tot = d * dout;
     if (tot == 0) return;
     build_transform_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(V, w, (int)d, (int)dout, T);
+    LAUNCH_CHECK();
+}
+
+// ================================================================================================ A * 1
+// rowscale[r] = sum of the row's Markov values in stored order (f32) -- the vector A*1 of the pipelined loop.
+__global__ void row_value_sums_kernel(const int64_t *__restrict__ rowptr, const float *__restrict__ val, int64_t n,
+                                      float *__restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float s = 0.f;
+    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) s = __fadd_rn(s, val[k]);
+    out[r] = s;
+}
+void launch_row_value_sums(const int64_t *rowptr, const float *val, int64_t n, float *out, cudaStream_t st) {
+    if (n == 0) return;
+    row_value_sums_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowptr, val, n, out);
     LAUNCH_CHECK();
 }
 

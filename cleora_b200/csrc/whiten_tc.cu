@@ -119,10 +119,14 @@ __global__ void prep_transform_kernel(const float *__restrict__ T, int d, int do
     base[chunk_floats + off] = lo;
 }
 
-template <int NORM>   // 0: none, 2: row L2 (x / max(norm, 1e-10)) fused into the epilogue
+// NORM: 0 none, 2 row L2 (x / max(norm, 1e-10)) fused into the epilogue.
+// SCALED: 0 -> a = x - mean;  1 -> a = x - rowscale[r] * mean  (x = A*Y with A not yet applied to the centring:
+//         A (Y - 1 mean^T) = A Y - (A 1) mean^T, rowscale = A 1; used by the pipelined loop, see abi.cu).
+template <int NORM, int SCALED>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const float *__restrict__ mean,
-                       const float *__restrict__ Bt, int N, float *__restrict__ out) {
+                       const float *__restrict__ rowscale, const float *__restrict__ Bt, int N,
+                       float *__restrict__ out) {
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b_bytes = N * BK * 4;                                  // one of hi / lo
@@ -162,6 +166,7 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
             const int64_t row = tile * BM + r;
             const bool in = row < n;
             const float4 *xr = reinterpret_cast<const float4 *>(x + (in ? row : 0) * (int64_t)d);
+            const float rs = (SCALED && in) ? __ldg(rowscale + row) : 1.f;
             for (int c = 0; c < n_chunks; ++c, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -174,7 +179,8 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
                 const int off = (r & 7) * 16 + (r >> 3) * 1024;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float4 m = __ldg(mp + q);
+                    float4 m = __ldg(mp + q);
+                    if (SCALED) { m.x = __fmul_rn(rs, m.x); m.y = __fmul_rn(rs, m.y); m.z = __fmul_rn(rs, m.z); m.w = __fmul_rn(rs, m.w); }
                     float4 a, h, l;
                     a.x = in ? __fsub_rn(v[q].x, m.x) : 0.f; a.y = in ? __fsub_rn(v[q].y, m.y) : 0.f;
                     a.z = in ? __fsub_rn(v[q].z, m.z) : 0.f; a.w = in ? __fsub_rn(v[q].w, m.w) : 0.f;
@@ -292,7 +298,7 @@ bool whiten_apply_tc_supported(int64_t d, int64_t dout) {
 
 // Scratch for the pre-tiled transform lives in the caller's workspace (misc).
 void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
-                            float *out, int norm, cudaStream_t st) {
+                            float *out, int norm, const float *rowscale, cudaStream_t st) {
     using namespace tc;
     if (n == 0) return;
     float *Bt = (float *)workspace().misc.get((size_t)2 * d * dout * sizeof(float));
@@ -303,15 +309,14 @@ void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *m
     const size_t smem = (size_t)STAGES * 2 * A_BYTES + (size_t)STAGES * 2 * N * BK * 4 + 16 * sizeof(uint64_t) + 16;
     const int64_t n_tiles = (n + BM - 1) / BM;
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
-    if (norm == CLEORA_NORM_L2_NUMPY) {
-        static bool attr = false;
-        if (!attr) { CUDA_TRY(cudaFuncSetAttribute(whiten_apply_tc_kernel<CLEORA_NORM_L2_NUMPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
-        whiten_apply_tc_kernel<CLEORA_NORM_L2_NUMPY><<<grid, THREADS, smem, st>>>(x, n, (int)d, mean_f32, Bt, N, out);
-    } else {
-        static bool attr = false;
-        if (!attr) { CUDA_TRY(cudaFuncSetAttribute(whiten_apply_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
-        whiten_apply_tc_kernel<0><<<grid, THREADS, smem, st>>>(x, n, (int)d, mean_f32, Bt, N, out);
-    }
+    auto launch = [&](auto kernel) {
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, mean_f32, rowscale, Bt, N, out);
+    };
+    const bool l2 = norm == CLEORA_NORM_L2_NUMPY;
+    if (norm != CLEORA_NORM_NONE && !l2) throw CudaFail{"tensor-core apply: unsupported fused normalisation"};
+    if (rowscale) { if (l2) launch(whiten_apply_tc_kernel<CLEORA_NORM_L2_NUMPY, 1>); else launch(whiten_apply_tc_kernel<0, 1>); }
+    else          { if (l2) launch(whiten_apply_tc_kernel<CLEORA_NORM_L2_NUMPY, 0>); else launch(whiten_apply_tc_kernel<0, 0>); }
     LAUNCH_CHECK();
 }
 

@@ -144,6 +144,11 @@ int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64_t iters, i
 typedef int (*cleora_eigh_fn)(double *a, double *w, int64_t d, void *user);
 void cleora_set_eigh(cleora_eigh_fn fn, void *user);
 
+/* Tuning switches.  "pipeline_whiten" (default 1): in cleora_embed's default configuration (whiten, l2, no residual,
+ * no early stop, d % 32 == 0, d <= 256) overlap the eigensolve with the next SpMM using
+ * A (Y - 1 mu^T) T = (A Y - (A 1) mu^T) T; 0 keeps the reference's stage order exactly. */
+int cleora_set_option(const char *key, int64_t value);
+
 /* Pinned host staging memory for callers that want async copies (bench e2e). */
 int cleora_host_alloc(size_t nbytes, void **out);
 void cleora_host_free(void *p);

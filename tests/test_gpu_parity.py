@@ -289,6 +289,24 @@ def test_teacher_forced_iteration_on_er_graph(er_pair):
     assert procrustes_err(z, z_ref) <= 1e-4
 
 
+def test_pipelined_loop_equals_reference_stage_order(er_pair):
+    """The default loop overlaps the eigensolve with the next SpMM through A(Y - 1 mu^T)T = (AY - (A1) mu^T)T
+    (abi.cu embed_pipelined); with the switch off the stages run in the reference's order.  Same mathematics."""
+    g, o = er_pair
+    try:
+        cb.set_option("pipeline_whiten", 0)
+        faithful = cb.embed(g, 64, 6)
+    finally:
+        cb.set_option("pipeline_whiten", 1)
+    piped = cb.embed(g, 64, 6)
+    ref = oracle.embed(o, 64, 6)
+    for got in (faithful, piped):
+        assert gram_err(got, ref) <= 1e-5
+        assert procrustes_err(got, ref) <= 1e-4
+    assert gram_err(piped, faithful) <= 1e-5
+    np.testing.assert_allclose(np.cov(piped.astype(np.float64), rowvar=False), np.eye(64), atol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 @pytest.fixture(scope="module")
 def big_graph():
