@@ -78,9 +78,14 @@ PROTOTYPES = {
     "cleora_dev_centered_gram": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cleora_dev_whiten_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_void_p, C.c_void_p]),
+    "cleora_dev_whiten_apply_ex": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                             C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "cleora_dev_row_scale": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "cleora_whiten_apply_fusable": (C.c_int, [C.c_int64, C.c_int64]),
     "cleora_dev_sq_diff_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "cleora_dev_whiten_transform": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "cleora_whiten_transform_from_cov": (C.c_int, [c_f64p, C.c_int64, C.c_int64, c_f32p]),
+    "cleora_release_workspace": (C.c_int, []),
     "cleora_dev_workspace_bytes": (C.c_int64, []),
     "cleora_kernel_launch_count": (C.c_int64, []),
 }

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <vector>
@@ -315,6 +316,27 @@ void whiten_device(const float *Y, int64_t n, int64_t d, int64_t dout, float *Z,
     ph.end(PH_APPLY);
 }
 
+// ---- per-thread persistent device state (cuSOLVER handle, whitening scratch, iterate buffers): creating these per
+// call costs ~0.2 s (cusolverDnCreate, four 1 GB cudaMallocs), measured; cleora_release_workspace() frees them.
+struct Persistent {
+    WhitenState ws;
+    DevBuf<float> buf[5];
+    float *get(int i, size_t count) {
+        if (buf[i].n < count) buf[i].alloc(count);
+        return buf[i].p;
+    }
+    void release() {
+        for (auto &b : buf) b.free();
+        ws.sums.free(); ws.cov.free(); ws.mean32.free(); ws.T.free();
+        ws.eig.evec.free(); ws.eig.eval.free(); ws.eig.work.free(); ws.eig.info.free();
+        ws.d = ws.dout = 0; ws.eig.d = 0;
+    }
+};
+Persistent &persistent() {
+    static thread_local Persistent p;
+    return p;
+}
+
 // ---- options -------------------------------------------------------------------------------------------------
 std::atomic<int> g_opt_pipeline{1};
 
@@ -347,7 +369,10 @@ struct SecondStream {
     cudaStream_t s = nullptr;
     cudaEvent_t stats_done = nullptr, t_ready = nullptr;
     SecondStream() {
-        CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        // highest priority: cuSOLVER's chain of small kernels must get SM slots ahead of the SpMM's 125k CTAs
+        int least = 0, greatest = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CUDA_TRY(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, greatest));
         CUDA_TRY(cudaEventCreateWithFlags(&stats_done, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&t_ready, cudaEventDisableTiming));
     }
@@ -368,7 +393,9 @@ bool pipeline_eligible(int64_t n, int64_t d, int64_t iters, int normalization, i
 void embed_pipelined(DeviceGraph &dg, const float *val, int markov, float *cur, float *y, float *w, float *y2, int64_t n,
                      int64_t d, int64_t iters, WhitenState &ws, Phase &ph, float **result) {
     cudaStream_t A = nullptr;
-    SecondStream B;
+    static thread_local std::unique_ptr<SecondStream> side;
+    if (!side) side.reset(new SecondStream());
+    SecondStream &B = *side;
     ws.ensure(d, d);
     const float *rowscale = row_scale_of(dg, markov);
     ph.begin();
@@ -436,7 +463,18 @@ extern "C" int cleora_host_alloc(size_t nbytes, void **out) {
     return guarded([&] { require_device(); CUDA_TRY(cudaMallocHost(out, nbytes ? nbytes : 1)); });
 }
 extern "C" void cleora_host_free(void *p) { if (p) cudaFreeHost(p); }
-extern "C" int64_t cleora_dev_workspace_bytes(void) { return (int64_t)workspace().bytes(); }
+extern "C" int64_t cleora_dev_workspace_bytes(void) {
+    int64_t t = (int64_t)workspace().bytes();
+    for (auto &b : persistent().buf) t += (int64_t)(b.n * sizeof(float));
+    return t;
+}
+extern "C" int cleora_release_workspace(void) {
+    return guarded([&] {
+        persistent().release();
+        Workspace &w = workspace();
+        w.colsum_partials.release(); w.gram_partials.release(); w.sqdiff_partials.release(); w.misc.release();
+    });
+}
 extern "C" int64_t cleora_kernel_launch_count(void) { return g_launches.load(); }
 
 // ================================================================================================ graph
@@ -608,6 +646,25 @@ extern "C" int cleora_dev_whiten_apply(const float *x, int64_t n, int64_t d, con
                                        int64_t dout, float *out, void *stream) {
     return guarded([&] { launch_whiten_apply(x, n, d, mean_f32, T, dout, out, (cudaStream_t)stream); });
 }
+extern "C" int cleora_dev_whiten_apply_ex(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
+                                          int64_t dout, float *out, int normalization, const float *rowscale,
+                                          void *stream) {
+    return guarded([&] {
+        if (normalization == CLEORA_NORM_NONE && rowscale == nullptr) {
+            launch_whiten_apply(x, n, d, mean_f32, T, dout, out, (cudaStream_t)stream);
+            return;
+        }
+        if (!whiten_apply_tc_supported(d, dout)) value_error("fused apply needs d % 32 == 0, dout % 16 == 0, dout <= 256");
+        launch_whiten_apply_tc(x, n, d, mean_f32, T, dout, out, normalization, rowscale, (cudaStream_t)stream);
+    });
+}
+extern "C" int cleora_dev_row_scale(cleora_graph_t *g, int markov, float *out, void *stream) {
+    return guarded([&] {
+        DeviceGraph &dg = device_graph(*g);
+        launch_row_value_sums(dg.rowptr, values_of(dg, markov), dg.n_rows, out, (cudaStream_t)stream);
+    });
+}
+extern "C" int cleora_whiten_apply_fusable(int64_t d, int64_t dout) { return whiten_apply_tc_supported(d, dout) ? 1 : 0; }
 extern "C" int cleora_dev_sq_diff_sum(const float *a, const float *b, int64_t n, int f64_diff, double *result,
                                       void *stream) {
     return guarded([&] { launch_sq_diff_sum(a, b, n, f64_diff != 0, result, (cudaStream_t)stream); });
@@ -685,9 +742,9 @@ static void embed_fast_impl(cleora_graph_t *g, int64_t d, int64_t iters, int mar
     if (!dg.hash && g->n_rows) value_error("graph has no entity hashes");
     const int64_t n = g->n_rows;
     const size_t cnt = (size_t)n * (size_t)d;
-    DevBuf<float> a(cnt), b(cnt);
+    Persistent &ps = persistent();
     DevBuf<double> dsum(1);
-    float *src = a.p, *dst = b.p;
+    float *src = ps.get(0, cnt), *dst = ps.get(1, cnt);
     launch_init(dg.hash, n, d, seed, src, nullptr);
     const bool use_res = rw > 0.0f && rw < 1.0f;                 // embedding.rs:116
     const float alpha = 1.0f - rw;
@@ -731,7 +788,7 @@ extern "C" int cleora_whiten_embeddings(const float *x, int64_t n, int64_t d, in
         }
         DevBuf<float> dx((size_t)n * d), dz((size_t)n * dout);
         CUDA_TRY(cudaMemcpy(dx.p, x, dx.n * sizeof(float), cudaMemcpyHostToDevice));
-        WhitenState ws;
+        WhitenState &ws = persistent().ws;
         Phase ph;
         whiten_device(dx.p, n, d, dout, dz.p, ws, nullptr, ph);
         CUDA_TRY(cudaMemcpy(out, dz.p, dz.n * sizeof(float), cudaMemcpyDeviceToHost));
@@ -756,10 +813,9 @@ extern "C" int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64
         if (timings_ms) std::fill(timings_ms, timings_ms + 8, 0.0);
         const bool conv = convergence_threshold > 0.0;
         const bool do_whiten = whiten != 0 && n > 1;
-        DevBuf<float> bx(cnt), by(cnt), bw;
-        if (conv && do_whiten) bw.alloc(cnt);
+        Persistent &ps = persistent();
         DevBuf<double> dsum(1);
-        float *cur = bx.p, *y = by.p, *w = bw.p;
+        float *cur = ps.get(0, cnt), *y = ps.get(1, cnt), *w = (conv && do_whiten) ? ps.get(2, cnt) : nullptr;
         if (x0) {
             ph.begin();
             CUDA_TRY(cudaMemcpyAsync(cur, x0, cnt * sizeof(float), cudaMemcpyDefault, nullptr));   // host or device
@@ -772,14 +828,12 @@ extern "C" int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64
         }
         const bool use_res = residual_weight > 0.0;              // pycleora/__init__.py:114 (no < 1 guard)
         const float alpha = (float)(1.0 - residual_weight), rwf = (float)residual_weight;
-        WhitenState ws;
+        WhitenState &ws = ps.ws;
         int64_t done = 0;
         float *result = cur;
         const bool pipelined = pipeline_eligible(n, d, iters, normalization, whiten, residual_weight, convergence_threshold);
-        DevBuf<float> bw2, by2;
         if (pipelined) {
-            bw2.alloc(cnt); by2.alloc(cnt);
-            embed_pipelined(dg, val, markov, cur, y, bw2.p, by2.p, n, d, iters, ws, ph, &result);
+            embed_pipelined(dg, val, markov, cur, y, ps.get(3, cnt), ps.get(4, cnt), n, d, iters, ws, ph, &result);
             done = iters;
         }
         for (int64_t it = 0; it < (pipelined ? 0 : iters); ++it) {

@@ -597,6 +597,7 @@ void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *me
     slices = std::max<int64_t>(1, (n + rows_per_slice - 1) / rows_per_slice);
     double *partial = (double *)workspace().gram_partials.get(size_t(slices) * size_t(d) * size_t(d) * sizeof(double));
     dim3 grid((unsigned)npairs, (unsigned)slices);
+    // (mma.sync.m16n8k16.f64 was tried: ptxas lowers it to the same DMMA.8x8x4 sequence on sm_100a -- no gain.)
     static const bool use_v3 = [] { const char *e = getenv("CLEORA_B200_GRAM"); return !(e && std::string(e) == "v2"); }();
     if (use_v3 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
         const size_t smem = (size_t)G3_STAGES * 2 * GK * G3_LD * sizeof(float);      // 69,632 B

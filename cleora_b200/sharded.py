@@ -139,6 +139,26 @@ class CudaBackend:
         """cov (device f64, scaled) -> T (device f32) on the current stream (cuSOLVER unless a host eigh is set)."""
         check(self.L.cleora_dev_whiten_transform(cov.data_ptr(), d, d, T.data_ptr(), self.stream()))
 
+    def fusable(self, d: int) -> bool:
+        return bool(self.L.cleora_whiten_apply_fusable(d, d))
+
+    def apply_ex(self, x, n, d, mean32, T, out, norm, rowscale):
+        check(self.L.cleora_dev_whiten_apply_ex(x.data_ptr(), n, d, mean32.data_ptr(), T.data_ptr(), d, out.data_ptr(),
+                                                norm, None if rowscale is None else rowscale.data_ptr(), self.stream()))
+
+    def row_scale(self, shard, markov, out):
+        check(self.L.cleora_dev_row_scale(shard.graph._handle(), markov, out.data_ptr(), self.stream()))
+
+    # streams: eigensolve / gather run beside the main stream in the pipelined loop
+    def new_stream(self):
+        return self.torch.cuda.Stream(device=self.device)
+
+    def on(self, stream):
+        return self.torch.cuda.stream(stream)
+
+    def current(self):
+        return self.torch.cuda.current_stream()
+
     def sync(self):
         self.torch.cuda.synchronize()
 
@@ -246,6 +266,90 @@ class ShardedEmbedder:
                     break
         return done
 
+    # ------------------------------------------------------------------------------------------ pipelined variant
+    def pipeline_eligible(self, iters, norm, residual_weight, convergence_threshold, whiten) -> bool:
+        return (bool(whiten) and self.shard.n > 1 and iters >= 2 and norm == _lib.NORM_L2_NUMPY
+                and residual_weight == 0 and convergence_threshold <= 0 and hasattr(self.be, "apply_ex")
+                and self.be.fusable(self.d) and os.environ.get("CLEORA_B200_PIPELINE", "1") != "0")
+
+    def _stats(self, y, timers=None):
+        """mean (self.sums, f64), mean32, cov (scaled) of the row-distributed matrix whose local block is y."""
+        be, s, d, n, dist = self.be, self.shard, self.d, self.shard.n, self.dist
+        t = timers.start("stats") if timers else None
+        be.col_sums(y, s.n_local, d, self.sums)
+        dist.all_reduce(self.sums, group=self.group)
+        self.sums.div_(float(n))
+        be.gram(y, s.n_local, d, self.sums, self.cov)
+        dist.all_reduce(self.cov, group=self.group)
+        self.cov.mul_(1.0 / float(n - 1))
+        self.mean32.copy_(self.sums)
+        if timers:
+            timers.stop(t)
+
+    def run_pipelined(self, iters: int, markov: int = 0, seed: int = 0, x0: Optional[np.ndarray] = None,
+                      timers=None) -> int:
+        """Same mathematics as run() for the default configuration, with the eigensolve (rank 0, side stream) hidden
+        behind the local SpMM via A (Y - 1 mu^T) T = (A Y - (A 1) mu^T) T, and the all-gather of the next iterate
+        (own communicator, own stream) hidden behind the covariance pass.  x_full holds the gathered NORMALISED
+        iterate Y between iterations; the final iterate X_T = (Y - 1 mu^T) T is gathered at the end."""
+        torch, dist, be, s, d = self.torch, self.dist, self.be, self.shard, self.d
+        if not hasattr(self, "_pl"):
+            side, comm = be.new_stream(), be.new_stream()
+            self._pl = dict(side=side, comm=comm, g_bcast=dist.new_group(), g_gather=dist.new_group(),
+                            w=be.empty((max(s.block, 1), d), torch.float32),
+                            rowscale=be.empty((max(s.block, 1),), torch.float32))
+            self._pl["w"].zero_()
+            self._pl["markov"] = None
+        pl = self._pl
+        side, comm, w, rowscale = pl["side"], pl["comm"], pl["w"], pl["rowscale"]
+        if pl["markov"] != markov:
+            be.row_scale(s, markov, rowscale)
+            pl["markov"] = markov
+        main = be.current()
+        if x0 is not None:
+            self.x_full.copy_(be.from_numpy(s.pad(np.ascontiguousarray(x0, np.float32))))
+        elif s.n_pad:
+            be.init(self.hash_pad, s.n_pad, d, seed, self.x_full)
+        # iteration 0: Y = rownorm(A X0); gather Y beside the stats
+        t = timers.start("spmm") if timers else None
+        be.spmm(s, markov, self.x_full, d, self.y, None, 1.0, 0.0, _lib.NORM_L2_NUMPY)
+        if timers:
+            timers.stop(t)
+        y, y2 = self.y, self.z
+        comm.wait_stream(main)
+        with be.on(comm):
+            dist.all_gather_into_tensor(self.x_full, y, group=pl["g_gather"])
+        self._stats(y, timers)
+        for it in range(1, iters):
+            side.wait_stream(main)                                   # cov of this iterate is ready
+            with be.on(side):
+                if s.rank == 0:
+                    be.transform(self.cov, d, self.T)
+                dist.broadcast(self.T, src=0, group=pl["g_bcast"])
+            main.wait_stream(comm)                                   # gathered Y is complete
+            t = timers.start("spmm") if timers else None
+            be.spmm(s, markov, self.x_full, d, w, None, 1.0, 0.0, _lib.NORM_NONE)      # W = A Y (own rows)
+            if timers:
+                timers.stop(t)
+            main.wait_stream(side)                                   # T has arrived
+            t = timers.start("apply") if timers else None
+            be.apply_ex(w, s.n_local, d, self.mean32, self.T, y2, _lib.NORM_L2_NUMPY, rowscale)
+            if timers:
+                timers.stop(t)
+            comm.wait_stream(main)
+            with be.on(comm):
+                dist.all_gather_into_tensor(self.x_full, y2, group=pl["g_gather"])     # next Y, beside the stats
+            self._stats(y2, timers)
+            y, y2 = y2, y
+        # final: X_T = (Y - 1 mu^T) T, gathered
+        if s.rank == 0:
+            be.transform(self.cov, d, self.T)
+        dist.broadcast(self.T, src=0, group=self.group)
+        main.wait_stream(comm)
+        be.apply(y, s.n_local, d, self.mean32, self.T, y2)
+        self._gather(y2)
+        return iters
+
     def result(self) -> np.ndarray:
         return self.shard.unpad(self.x_full.cpu().numpy())
 
@@ -267,8 +371,12 @@ def embed_sharded(graph: SparseMatrix, feature_dim: int = 256, num_iterations: i
     d = feature_dim if initial_embeddings is None else initial_embeddings.shape[1]
     rust = initial_embeddings is None and normalization == "l2" and not whiten
     em = ShardedEmbedder(shard, d, backend=backend, group=group)
-    em.run(num_iterations, _lib.MARKOV[propagation], _lib.NORM_L2_RUST if rust else norms[normalization], seed,
-           initial_embeddings, residual_weight, convergence_threshold, whiten, rust_semantics=rust)
+    norm = _lib.NORM_L2_RUST if rust else norms[normalization]
+    if em.pipeline_eligible(num_iterations, norm, residual_weight, convergence_threshold, whiten):
+        em.run_pipelined(num_iterations, _lib.MARKOV[propagation], seed, initial_embeddings)
+    else:
+        em.run(num_iterations, _lib.MARKOV[propagation], norm, seed, initial_embeddings, residual_weight,
+               convergence_threshold, whiten, rust_semantics=rust)
     return em.result()
 
 
@@ -327,8 +435,13 @@ def bench(args, w, name, gen_pairs, spmm_bytes, measured_peaks, ClockSampler):
         shutil.rmtree(tag, ignore_errors=True)
     norm = _lib.NORM_L2_NUMPY if args.whiten else _lib.NORM_L2_RUST
 
+    piped = em.pipeline_eligible(iters, norm, 0.0, 0.0, bool(args.whiten))
+
     def step(timers=None):
-        em.run(iters, 0, norm, 0, None, 0.0, 0.0, bool(args.whiten), rust_semantics=not args.whiten, timers=timers)
+        if piped:
+            em.run_pipelined(iters, 0, 0, None, timers=timers)
+        else:
+            em.run(iters, 0, norm, 0, None, 0.0, 0.0, bool(args.whiten), rust_semantics=not args.whiten, timers=timers)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -383,7 +496,8 @@ def bench(args, w, name, gen_pairs, spmm_bytes, measured_peaks, ClockSampler):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "nodes": n, "edges": E, "nnz": nnz, "d": d, "iters": iters,
-                       "whiten": bool(args.whiten), "parallelism": f"row-shard x{world} (nnz-balanced)",
+                       "whiten": bool(args.whiten), "pipeline_whiten": bool(piped),
+                       "parallelism": f"row-shard x{world} (nnz-balanced)",
                        "collectives": "NCCL all-gather of X blocks per iteration; all-reduce of d+d*d f64; T broadcast",
                        "l2_flush": "inputs exceed the 126 MB L2"},
             "nnz_per_s": nnz * iters / (ms_step * 1e-3),

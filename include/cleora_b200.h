@@ -176,6 +176,15 @@ int cleora_dev_centered_gram(const float *x, int64_t n, int64_t d, const double 
 /* K3: out[n, dout] = (x[n, d] - mean_f32[d]) @ T[d, dout]  (f32). */
 int cleora_dev_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
                             int64_t dout, float *out, void *stream);
+/* K3 with the pipelined loop's extras: out = rownorm_or_not( (x - rowscale[r] * mean_f32) @ T ).  `rowscale` NULL = 1;
+ * `normalization` CLEORA_NORM_NONE or CLEORA_NORM_L2_NUMPY (fused in the tensor-core epilogue; needs the tcgen05
+ * shape rules d % 32 == 0, dout % 16 == 0, dout <= 256, otherwise CLEORA_ERR_VALUE). */
+int cleora_dev_whiten_apply_ex(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
+                               int64_t dout, float *out, int normalization, const float *rowscale, void *stream);
+/* rowscale[r] = sum of the Markov values of row r (the vector A*1), f32 [n_rows], device. */
+int cleora_dev_row_scale(cleora_graph_t *g, int markov, float *out, void *stream);
+/* 1 if cleora_dev_whiten_apply_ex can fuse (tensor-core path available for this shape), else 0. */
+int cleora_whiten_apply_fusable(int64_t d, int64_t dout);
 /* sum((a - b)^2) over n elements, f64 accumulation; result[0] overwritten.  f64_diff == 0: f32 difference and
  * square (src/embedding.rs:173-174); != 0: f64 difference and square (pycleora/__init__.py:975-976). */
 int cleora_dev_sq_diff_sum(const float *a, const float *b, int64_t n, int f64_diff, double *result, void *stream);
@@ -185,6 +194,9 @@ int cleora_dev_sq_diff_sum(const float *a, const float *b, int64_t n, int f64_di
 int cleora_dev_whiten_transform(const double *cov, int64_t d, int64_t dout, float *T, void *stream);
 /* Host step of the whitening: cov (f64, already divided by n-1) -> T (f32 [d, dout]) via the installed eigh. */
 int cleora_whiten_transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T);
+/* The calling thread keeps its iterate buffers, whitening scratch and cuSOLVER handle between calls (re-creating
+ * them costs ~0.2 s per call); this frees them. */
+int cleora_release_workspace(void);
 /* Bytes of device scratch currently held by the calling thread's workspace (diagnostics). */
 int64_t cleora_dev_workspace_bytes(void);
 /* Number of kernel launches issued by this library since process start (bench's gpu_launches). */
