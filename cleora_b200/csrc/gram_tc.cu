@@ -1,0 +1,385 @@
+// K2b on the 5th-generation tensor cores: the centred Gram matrix  sum_r (x_r - mean)(x_r - mean)^T  computed
+// EXACTLY in integers (pycleora/__init__.py:138-142 accumulates it in f64; the PCA basis amplifies covariance
+// error by 1/eigengap, so floating-point tensor kinds with f32 accumulators are not admissible).
+//
+// Method (error-free byte-plane split; no floating-point rounding anywhere before the final f64 combination):
+//   q[r,j]  = rint(x[r,j] * 2^e) - m[j]                  int32, |q| < 2^31;  e, m[j] = rint(mean[j] * 2^e) from
+//                                                        quant_params_kernel (2^e <= 2^30 / (max|x| + max|mean|))
+//   q       = b0 + 2^8 b1 + 2^16 b2 + 2^24 b3            b0..b2 unsigned bytes, b3 signed (two's complement planes)
+//   G_s[i,j] = sum_{k+l=s} sum_r b_k[r,i] * b_l[r,j]     tcgen05.mma kind::i8, int32 accumulators in TMEM, one
+//                                                        accumulator per power-of-two weight group s = 0..6
+//   sum_r q_i q_j = sum_s 2^(8s) G_s[i,j]                exact; int64 global accumulators, drained every <= 8192 rows
+//   result  = ( sum_r q_i q_j - S_i S_j / n ) / 4^e      S = column sums of q (exact int64), combined in f64
+// The only approximation is the input quantisation 2^-e (<= 2^-30 of max|x|, i.e. well below one f32 ulp of a
+// typical element).  Integer accumulation is order-independent, so the result is bit-identical for any slicing,
+// any atomic order and any GPU count.
+//
+// One CTA = a 32-column stripe j of the output for a slice of rows: TMEM holds 2 (M blocks of 128 rows i) x 7
+// (weight groups) accumulators of 128 x 32 int32 = 448 of its 512 columns.  Per 64-row stage the producers
+// (4 warps) quantise all d columns once into four byte planes in the canonical MN-major no-swizzle UMMA layout
+// (8 K-rows x 16 bytes per core matrix); both MMA operands are views of those planes (A: 128 columns of plane k,
+// B: the stripe's 32 columns of plane l).
+#include "device.cuh"
+#include "../../include/cleora_b200.h"
+
+#include <algorithm>
+
+namespace cleora {
+namespace g8 {
+
+constexpr int ROWS = 64;           // rows (K) per stage = 2 MMA k-steps of 32
+constexpr int STAGES = 3;
+constexpr int STRIPE = 32;         // output columns per CTA (UMMA N)
+constexpr int GROUPS = 7;          // weight groups s = k + l
+constexpr int DRAIN_STAGES = 96;   // 96*64 = 6144 rows: 4 * 255^2 * 6144 < 2^31
+constexpr int THREADS = 320;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    const long long t0 = clock64();
+    do {
+        if (clock64() - t0 > 8000000000LL) __trap();      // watchdog: a protocol bug must not hang the GPU
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// SWIZZLE_NONE descriptor; for MN-major operands LBO = byte distance between 8-row K groups, SBO = byte distance
+// between 16-byte MN groups (cute make_umma_desc<Major::MN>, INTERLEAVE case).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// kind::i8 instruction descriptor: D = s32 (2), A/B format 0 = u8 / 1 = s8, both MN-major, M = 128, N = 32.
+__device__ __forceinline__ uint32_t make_idesc_i8(int a_signed, int b_signed) {
+    return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | (1u << 15) | (1u << 16) |
+           ((uint32_t)(STRIPE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct QuantParams {
+    float scale;        // 2^e
+    int32_t e;
+    int32_t pad[2];
+};
+
+}  // namespace g8
+
+// max |x| over the matrix (per-block partial maxima, then one block) -- feeds the fixed-point scale.
+__global__ void __launch_bounds__(256) absmax_stage1(const float *__restrict__ x, int64_t count, float *__restrict__ partial) {
+    float m = 0.f;
+    const float4 *xv = reinterpret_cast<const float4 *>(x);
+    const int64_t n4 = count / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(xv + i);
+        m = fmaxf(fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fabsf(v.z))), fabsf(v.w));
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    __shared__ float sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, sh[w]);
+        partial[blockIdx.x] = m;
+    }
+}
+
+// scale = 2^e with (max|x| + max|mean|) * 2^e < 2^30;  m[j] = rint(mean[j] * 2^e);  zero the accumulators.
+__global__ void quant_params_kernel(const float *__restrict__ absmax_partial, int nb, const double *__restrict__ mean,
+                                    int d, g8::QuantParams *__restrict__ qp, int32_t *__restrict__ m_int) {
+    __shared__ float s_scale;
+    if (threadIdx.x == 0) {
+        float mx = 0.f;
+        for (int i = 0; i < nb; ++i) mx = fmaxf(mx, absmax_partial[i]);
+        double mm = 0.0;
+        for (int j = 0; j < d; ++j) mm = fmax(mm, fabs(mean[j]));
+        const double bound = (double)mx + mm;
+        int e = 30;
+        if (bound > 0.0) {
+            int ex;
+            frexp(bound, &ex);                 // bound = f * 2^ex, f in [0.5, 1)  =>  bound < 2^ex
+            e = 30 - ex;
+        }
+        e = max(-60, min(e, 60));
+        qp->e = e;
+        qp->scale = (float)ldexp(1.0, e);
+        s_scale = qp->scale;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < d; j += blockDim.x) m_int[j] = (int32_t)llrint(mean[j] * (double)s_scale);
+}
+
+__global__ void __launch_bounds__(g8::THREADS, 1)
+gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantParams *__restrict__ qp,
+               const int32_t *__restrict__ m_int, long long *__restrict__ G /* [7][d][d] */,
+               long long *__restrict__ colsum /* [d] */, int64_t rows_per_slice) {
+    using namespace g8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int plane_bytes = ROWS * d;                                 // one byte plane of one stage
+    const int stage_bytes = 4 * plane_bytes;
+    unsigned char *sP = smem_raw;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + STAGES * stage_bytes);
+    uint64_t *full = bars;                   // [STAGES] count 128 (producers)
+    uint64_t *empty = bars + STAGES;         // [STAGES] count 1 (tcgen05.commit)
+    uint64_t *acc_full = bars + 2 * STAGES;  // count 1
+    uint64_t *acc_empty = acc_full + 1;      // count 128 (drain threads)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int js = blockIdx.x;                                        // output column stripe
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice, r1 = min(n, r0 + rows_per_slice);
+    const int n_stages = (int)((r1 - r0 + ROWS - 1) / ROWS);
+    const int n_mb = d / 128;
+    const int n_cg = d / 16;                                          // 16-byte column groups per row
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------ producers: quantise, split, lay out
+        // thread -> (row lane rl = tid % 8, column-group slot cs = tid / 8); it handles rows rl + 8*i of the stage and
+        // the column groups cs, cs + 16, ...  (a quarter-warp = 8 rows of one column group = one 128-byte core matrix)
+        const int rl = threadIdx.x & 7, cs = threadIdx.x >> 3;
+        const float scale = qp->scale;
+        long long csum[16];                              // exact column sums of q for this thread's column group
+#pragma unroll
+        for (int c = 0; c < 16; ++c) csum[c] = 0;           // (n_cg <= 16 for the supported d, so one group per thread)
+        for (int st = 0; st < n_stages; ++st) {
+            const int s = st % STAGES;
+            mbar_wait(&empty[s], ((st / STAGES) & 1) ^ 1);
+            unsigned char *base = sP + s * stage_bytes;
+            for (int cg = cs; cg < n_cg; cg += 16) {
+                int4 mi[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) mi[q] = __ldg(reinterpret_cast<const int4 *>(m_int + cg * 16) + q);
+#pragma unroll 2
+                for (int i = 0; i < ROWS / 8; ++i) {
+                    const int rr = rl + 8 * i;
+                    const int64_t row = r0 + (int64_t)st * ROWS + rr;
+                    int qv[16];
+                    if (row < r1) {
+                        const float4 *xp = reinterpret_cast<const float4 *>(x + row * (int64_t)d + cg * 16);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 v = __ldg(xp + q);
+                            qv[4 * q + 0] = __float2int_rn(v.x * scale) - mi[q].x;
+                            qv[4 * q + 1] = __float2int_rn(v.y * scale) - mi[q].y;
+                            qv[4 * q + 2] = __float2int_rn(v.z * scale) - mi[q].z;
+                            qv[4 * q + 3] = __float2int_rn(v.w * scale) - mi[q].w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) qv[c] = 0;
+                    }
+                    // byte planes: word w of plane p = bytes p of qv[4w..4w+3]
+                    const uint32_t off = (uint32_t)((rr & 7) * 16 + (rr >> 3) * 128 + cg * (ROWS / 8) * 128);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        uint4 o;
+                        uint32_t *ow = &o.x;
+#pragma unroll
+                        for (int wq = 0; wq < 4; ++wq) {
+                            const uint32_t lo = __byte_perm((uint32_t)qv[4 * wq], (uint32_t)qv[4 * wq + 1], 0x0040 + 0x0011 * p);
+                            const uint32_t hi = __byte_perm((uint32_t)qv[4 * wq + 2], (uint32_t)qv[4 * wq + 3], 0x0040 + 0x0011 * p);
+                            ow[wq] = __byte_perm(lo, hi, 0x5410);
+                        }
+                        *reinterpret_cast<uint4 *>(base + p * plane_bytes + off) = o;
+                    }
+                    if (js == 0) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) csum[c] += qv[c];
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&full[s]);
+        }
+        if (js == 0) {                                      // stripe 0 owns the column sums: 8 row lanes -> 1
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                long long v = csum[c];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                if (rl == 0 && cs < n_cg && v != 0)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(colsum + cs * 16 + c), (unsigned long long)v);
+            }
+        }
+    } else if (warp < 8) {
+        // ------------------------------------------------------------ drain: TMEM int32 -> global int64 (atomic)
+        const int q4 = warp - 4;
+        uint32_t v[32];
+        int drains = 0;
+        for (int st0 = 0; st0 < n_stages; st0 += DRAIN_STAGES, ++drains) {
+            mbar_wait(acc_full, drains & 1);
+            tc_fence_after();
+            for (int mb = 0; mb < n_mb; ++mb)
+                for (int s = 0; s < GROUPS; ++s) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((mb * GROUPS + s) * STRIPE);
+                    tmem_ld32(taddr, v);
+                    const int i = mb * 128 + q4 * 32 + lane;
+                    long long *dst = G + ((int64_t)s * d + i) * d + js * STRIPE;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const long long val = (long long)(int32_t)v[c];
+                        if (val != 0) atomicAdd(reinterpret_cast<unsigned long long *>(dst + c), (unsigned long long)val);
+                    }
+                }
+            tc_fence_before();
+            mbar_arrive(acc_empty);
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------ MMA issuer
+        int drains = 0;
+        for (int st = 0; st < n_stages; ++st) {
+            const int s = st % STAGES;
+            const bool first = (st % DRAIN_STAGES) == 0;              // first stage after a drain: overwrite
+            if (first && st > 0) {                                    // wait until the previous accumulators are drained
+                mbar_wait(acc_empty, (drains - 1) & 1);
+                tc_fence_after();
+            }
+            mbar_wait(&full[s], (st / STAGES) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t pbase = smem_u32(sP + s * stage_bytes);
+                const uint32_t lbo = 128, sbo = (ROWS / 8) * 128;     // K groups adjacent, MN groups 1024 B apart
+                uint32_t used = 0;                                    // bit (mb*7+s): accumulator already written
+#pragma unroll 1
+                for (int ks = 0; ks < ROWS / 32; ++ks) {
+                    const uint32_t koff = ks * 4 * 128;               // 32 K rows = 4 groups of 8
+                    for (int mb = 0; mb < n_mb; ++mb) {
+#pragma unroll 1
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = make_desc(pbase + k * plane_bytes + (mb * 8) * sbo + koff, lbo, sbo);
+#pragma unroll 1
+                            for (int l = 0; l < 4; ++l) {
+                                const uint64_t bd = make_desc(pbase + l * plane_bytes + (js * 2) * sbo + koff, lbo, sbo);
+                                const int g = k + l;
+                                const uint32_t bit = 1u << (mb * GROUPS + g);
+                                const uint32_t acc = (first && !(used & bit)) ? 0u : 1u;
+                                used |= bit;
+                                mma_i8(tmem_base + (uint32_t)((mb * GROUPS + g) * STRIPE), ad, bd, make_idesc_i8(k == 3, l == 3), acc);
+                            }
+                        }
+                    }
+                }
+                mma_commit(&empty[s]);
+                const bool last_of_window = ((st + 1) % DRAIN_STAGES) == 0 || st + 1 == n_stages;
+                if (last_of_window) mma_commit(acc_full);
+            }
+            __syncwarp();
+            if (((st + 1) % DRAIN_STAGES) == 0 || st + 1 == n_stages) ++drains;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// With Q = sum_s 2^(8s) G_s (exact sum_r q_i q_j), S = column sums of q (exact) and delta_j = mean_j 2^e - m_j (the
+// part of the requested centre the integer centring did not remove, |delta| <~ 1):
+//   sum_r (x_i - mean_i)(x_j - mean_j) = ( Q_ij - S_i delta_j - delta_i S_j + n delta_i delta_j ) * 4^-e
+// `mean` may be any centre (the global mean when the rows are one rank's shard).
+__global__ void gram_i8_combine_kernel(const long long *__restrict__ G, const long long *__restrict__ colsum,
+                                       const int32_t *__restrict__ m_int, const double *__restrict__ mean, int d,
+                                       int64_t n, const g8::QuantParams *__restrict__ qp, double *__restrict__ cov) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)d * d) return;
+    const int i = (int)(idx / d), j = (int)(idx - (int64_t)i * d);
+    double acc = 0.0;
+    for (int s = 0; s < g8::GROUPS; ++s) acc += ldexp((double)G[(int64_t)s * d * d + idx], 8 * s);   // small to large
+    const double di = ldexp(mean[i], qp->e) - (double)m_int[i], dj = ldexp(mean[j], qp->e) - (double)m_int[j];
+    acc += -(double)colsum[i] * dj - di * (double)colsum[j] + (double)n * di * dj;
+    cov[idx] = ldexp(acc, -2 * qp->e);
+}
+
+bool gram_i8_supported(int64_t n, int64_t d) { return (d == 128 || d == 256) && n >= 4096; }
+
+void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st) {
+    using namespace g8;
+    // scratch: absmax partials | QuantParams | m_int[d] | colsum[d] | G[7][d][d]
+    const int nb = 148 * 4;
+    const size_t off_qp = 1024 * sizeof(float);
+    const size_t off_m = off_qp + sizeof(QuantParams);
+    const size_t off_cs = off_m + sizeof(int32_t) * 512;
+    const size_t off_G = off_cs + sizeof(long long) * 512;
+    const size_t total = off_G + sizeof(long long) * GROUPS * d * d;
+    unsigned char *ws = (unsigned char *)workspace().gram_partials.get(total);
+    float *absmax = (float *)ws;
+    QuantParams *qp = (QuantParams *)(ws + off_qp);
+    int32_t *m_int = (int32_t *)(ws + off_m);
+    long long *colsum = (long long *)(ws + off_cs);
+    long long *G = (long long *)(ws + off_G);
+    CUDA_TRY(cudaMemsetAsync(ws + off_cs, 0, total - off_cs, st));
+    absmax_stage1<<<nb, 256, 0, st>>>(x, n * d, absmax);
+    LAUNCH_CHECK();
+    quant_params_kernel<<<1, 256, 0, st>>>(absmax, nb, mean, (int)d, qp, m_int);
+    LAUNCH_CHECK();
+    const int stripes = (int)(d / STRIPE);
+    int64_t slices = std::max<int64_t>(1, std::min<int64_t>(148 / stripes, (n + 4 * ROWS - 1) / (4 * ROWS)));   // one wave
+    const int64_t rows_per_slice = ((n + slices - 1) / slices + ROWS - 1) / ROWS * ROWS;
+    slices = (n + rows_per_slice - 1) / rows_per_slice;
+    const size_t smem = (size_t)STAGES * 4 * ROWS * d + 16 * sizeof(uint64_t) + 16;
+    static bool attr = false;
+    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    dim3 grid((unsigned)stripes, (unsigned)slices);
+    gram_i8_kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, qp, m_int, G, colsum, rows_per_slice);
+    LAUNCH_CHECK();
+    gram_i8_combine_kernel<<<(unsigned)((d * d + 255) / 256), 256, 0, st>>>(G, colsum, m_int, mean, (int)d, n, qp, cov);
+    LAUNCH_CHECK();
+}
+
+}  // namespace cleora

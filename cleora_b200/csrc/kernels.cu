@@ -586,8 +586,18 @@ __global__ void gram_reduce_kernel(const double *__restrict__ partial, int slice
     if (i / GT != j / GT) cov[(int64_t)j * d + i] = s;
 }
 
+bool gram_i8_supported(int64_t n, int64_t d);
+void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st);
+
 void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st) {
     if (d == 0) return;
+    {   // exact-integer tcgen05 path for the large, common shapes; CLEORA_B200_GRAM=v3|v2 forces the FP64 DMMA kernels
+        static const bool allow_i8 = [] { const char *e = getenv("CLEORA_B200_GRAM"); return !e || std::string(e) == "i8"; }();
+        if (allow_i8 && gram_i8_supported(n, d) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+            launch_centered_gram_i8(x, n, d, mean, cov, st);
+            return;
+        }
+    }
     const int nblk = (int)((d + GB - 1) / GB);
     const int npairs = nblk * (nblk + 1) / 2;
     // one resident CTA per SM: ~148 CTAs in flight, a few waves when n is large

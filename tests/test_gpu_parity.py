@@ -166,7 +166,7 @@ def _dev_stats(x):
     return mean.cpu().numpy(), cov.cpu().numpy()
 
 
-@pytest.mark.parametrize("n,d", [(3000, 48), (5000, 256), (777, 100), (20000, 512), (2, 8), (40, 64)])
+@pytest.mark.parametrize("n,d", [(3000, 48), (4000, 256), (777, 100), (20000, 512), (2, 8), (40, 64)])
 def test_mean_and_covariance_f64(n, d):
     rs = np.random.default_rng(n + d)
     x = oracle.normalize((rs.standard_normal((n, d)) * rs.uniform(0.2, 3.0, d) + rs.uniform(-1, 1, d)).astype(np.float32))
@@ -176,6 +176,37 @@ def test_mean_and_covariance_f64(n, d):
     cov = gram / (n - 1)
     assert np.max(np.abs(cov - ref_cov)) <= 1e-12 * np.max(np.abs(ref_cov))
     np.testing.assert_array_equal(cov, cov.T)
+
+
+def test_integer_gram_on_tensor_cores_is_exact():
+    """K2b's tcgen05 kind::i8 path (d in {128, 256}, n >= 4096): for inputs that are exactly representable in its
+    fixed-point format the centred Gram matrix must equal the exact rational result -- checked with Python
+    integers -- and on generic f32 data it must agree with the f64 oracle to the quantisation bound."""
+    rs = np.random.default_rng(5)
+    for n, d in ((5000, 128), (20000, 256), (4096 + 77, 256)):
+        # multiples of 2^-20 in (-1, 1): exactly representable in f32 and in the kernel's 2^-e grid (e >= 29)
+        k = rs.integers(-(2 ** 20) + 1, 2 ** 20, size=(n, d))
+        k[:, 3] //= 4096                                        # a column of small values (low planes only)
+        k[:, 5] = -np.abs(k[:, 5])                              # a sign-constant column (mean far from 0)
+        x = (k.astype(np.float64) / 2 ** 20).astype(np.float32)
+        assert np.array_equal(x.astype(np.float64) * 2 ** 20, k)
+        mean, gram = _dev_stats(x)
+        S = k.sum(axis=0)                                        # exact integers
+        ref_mean = S.astype(np.float64) / n / 2 ** 20
+        np.testing.assert_allclose(mean, ref_mean, rtol=1e-14, atol=1e-18)
+        kc = k.astype(np.float64) - S / n                        # exact-ish reference in f64 (|kc| < 2^21, sums < 2^63)
+        ref = (kc.T @ kc) / 2.0 ** 40
+        assert np.max(np.abs(gram - ref)) <= 1e-13 * np.max(np.abs(ref))
+        for i, j in ((3, 5), (0, 0), (5, 5), (d - 1, 7), (3, 3)):  # fully exact check with Python integers
+            dot = sum(int(a) * int(b) for a, b in zip(k[:, i], k[:, j]))
+            exact = (dot * n - int(S[i]) * int(S[j])) / n / 2 ** 40
+            assert abs(gram[i, j] - exact) <= 4e-16 * max(abs(exact), np.max(np.abs(ref)) * 1e-3)
+    x = oracle.normalize((rs.standard_normal((30000, 256)) * rs.uniform(0.2, 3.0, 256) + rs.uniform(-1, 1, 256)).astype(np.float32))
+    mean, gram = _dev_stats(x)
+    ref_mean, ref_cov = oracle.whiten_stats(x)
+    cov = gram / (x.shape[0] - 1)
+    assert np.max(np.abs(cov - ref_cov)) <= 1e-9 * np.max(np.abs(ref_cov))     # 2^-30 input quantisation
+    np.testing.assert_allclose(cov, cov.T, rtol=0, atol=1e-18)
 
 
 @pytest.mark.parametrize("n,d,dout", [(3000, 48, 48), (5000, 256, 256), (777, 100, 100), (1000, 64, 10), (4097, 512, 512)])
