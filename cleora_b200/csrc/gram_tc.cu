@@ -27,11 +27,12 @@
 namespace cleora {
 namespace g8 {
 
-constexpr int ROWS = 64;           // rows (K) per stage = 2 MMA k-steps of 32
+constexpr int ROWS = 32;           // rows (K) per stage = one MMA k-step
 constexpr int STAGES = 3;
+constexpr int RAW_PAD = 16;        // raw f32 rows are staged with a 16-byte skew: conflict-free LDS.128 across rows
 constexpr int STRIPE = 32;         // output columns per CTA (UMMA N)
 constexpr int GROUPS = 7;          // weight groups s = k + l
-constexpr int DRAIN_STAGES = 96;   // 96*64 = 6144 rows: 4 * 255^2 * 6144 < 2^31
+constexpr int DRAIN_STAGES = 192;  // 192*32 = 6144 rows: 4 * 255^2 * 6144 < 2^31
 constexpr int THREADS = 320;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -54,6 +55,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
     } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -154,12 +163,17 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int plane_bytes = ROWS * d;                                 // one byte plane of one stage
     const int stage_bytes = 4 * plane_bytes;
-    unsigned char *sP = smem_raw;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + STAGES * stage_bytes);
-    uint64_t *full = bars;                   // [STAGES] count 128 (producers)
-    uint64_t *empty = bars + STAGES;         // [STAGES] count 1 (tcgen05.commit)
-    uint64_t *acc_full = bars + 2 * STAGES;  // count 1
-    uint64_t *acc_empty = acc_full + 1;      // count 128 (drain threads)
+    const int raw_stride = d * 4 + RAW_PAD;                           // bytes per staged f32 row
+    const int raw_bytes = ROWS * raw_stride;
+    unsigned char *sP = smem_raw;                                     // [STAGES] byte planes (MMA operands)
+    unsigned char *sR = sP + STAGES * stage_bytes;                    // [STAGES] raw f32 rows (TMA destination)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sR + STAGES * raw_bytes);
+    uint64_t *raw_full = bars;                   // [STAGES] count 1 + tx bytes (TMA)
+    uint64_t *raw_empty = bars + STAGES;         // [STAGES] count 128 (converters)
+    uint64_t *full = bars + 2 * STAGES;          // [STAGES] count 128 (converters): planes ready
+    uint64_t *empty = bars + 3 * STAGES;         // [STAGES] count 1 (tcgen05.commit): planes consumed
+    uint64_t *acc_full = bars + 4 * STAGES;      // count 1
+    uint64_t *acc_empty = acc_full + 1;          // count 128 (drain threads)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -170,7 +184,9 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     const int n_cg = d / 16;                                          // 16-byte column groups per row
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); mbar_init(&full[s], 128); mbar_init(&empty[s], 1);
+        }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -185,32 +201,37 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // ------------------------------------------------------------ producers: quantise, split, lay out
-        // thread -> (row lane rl = tid % 8, column-group slot cs = tid / 8); it handles rows rl + 8*i of the stage and
-        // the column groups cs, cs + 16, ...  (a quarter-warp = 8 rows of one column group = one 128-byte core matrix)
+        // ------------------------------------------------------------ converters: raw f32 (smem) -> 4 byte planes
+        // thread -> (row lane rl = tid % 8, column group cs = tid / 8); rows rl + 8*i of the stage.  A quarter-warp =
+        // 8 rows of one column group = one 128-byte core matrix (conflict-free STS.128); the raw rows are skewed by 16
+        // bytes so the 8 LDS.128 of a quarter-warp hit distinct banks as well.
         const int rl = threadIdx.x & 7, cs = threadIdx.x >> 3;
+        const bool has_cg = cs < n_cg;
         const float scale = qp->scale;
+        int4 mi[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mi[q] = has_cg ? __ldg(reinterpret_cast<const int4 *>(m_int + cs * 16) + q) : make_int4(0, 0, 0, 0);
         long long csum[16];                              // exact column sums of q for this thread's column group
 #pragma unroll
-        for (int c = 0; c < 16; ++c) csum[c] = 0;           // (n_cg <= 16 for the supported d, so one group per thread)
+        for (int c = 0; c < 16; ++c) csum[c] = 0;
         for (int st = 0; st < n_stages; ++st) {
             const int s = st % STAGES;
-            mbar_wait(&empty[s], ((st / STAGES) & 1) ^ 1);
+            const uint32_t ph = (st / STAGES) & 1;
+            mbar_wait(&raw_full[s], ph);                 // TMA has landed this stage's rows
+            mbar_wait(&empty[s], ph ^ 1);                // the MMAs that read these planes last time have retired
+            const unsigned char *raw = sR + s * raw_bytes;
             unsigned char *base = sP + s * stage_bytes;
-            for (int cg = cs; cg < n_cg; cg += 16) {
-                int4 mi[4];
+            if (has_cg) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) mi[q] = __ldg(reinterpret_cast<const int4 *>(m_int + cg * 16) + q);
-#pragma unroll 2
                 for (int i = 0; i < ROWS / 8; ++i) {
                     const int rr = rl + 8 * i;
                     const int64_t row = r0 + (int64_t)st * ROWS + rr;
                     int qv[16];
                     if (row < r1) {
-                        const float4 *xp = reinterpret_cast<const float4 *>(x + row * (int64_t)d + cg * 16);
+                        const float4 *xp = reinterpret_cast<const float4 *>(raw + rr * raw_stride + cs * 64);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 v = __ldg(xp + q);
+                            const float4 v = xp[q];
                             qv[4 * q + 0] = __float2int_rn(v.x * scale) - mi[q].x;
                             qv[4 * q + 1] = __float2int_rn(v.y * scale) - mi[q].y;
                             qv[4 * q + 2] = __float2int_rn(v.z * scale) - mi[q].z;
@@ -220,10 +241,9 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
 #pragma unroll
                         for (int c = 0; c < 16; ++c) qv[c] = 0;
                     }
-                    // byte planes: word w of plane p = bytes p of qv[4w..4w+3]
-                    const uint32_t off = (uint32_t)((rr & 7) * 16 + (rr >> 3) * 128 + cg * (ROWS / 8) * 128);
+                    const uint32_t off = (uint32_t)((rr & 7) * 16 + (rr >> 3) * 128 + cs * (ROWS / 8) * 128);
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
+                    for (int p = 0; p < 4; ++p) {        // word w of plane p = byte p of qv[4w .. 4w+3]
                         uint4 o;
                         uint32_t *ow = &o.x;
 #pragma unroll
@@ -242,6 +262,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             }
             fence_proxy_async();
             mbar_arrive(&full[s]);
+            mbar_arrive(&raw_empty[s]);
         }
         if (js == 0) {                                      // stripe 0 owns the column sums: 8 row lanes -> 1
 #pragma unroll
@@ -250,7 +271,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
                 v += __shfl_xor_sync(0xffffffffu, v, 4);
-                if (rl == 0 && cs < n_cg && v != 0)
+                if (rl == 0 && has_cg && v != 0)
                     atomicAdd(reinterpret_cast<unsigned long long *>(colsum + cs * 16 + c), (unsigned long long)v);
             }
         }
@@ -280,6 +301,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     } else if (warp == 8) {
         // ------------------------------------------------------------ MMA issuer
         int drains = 0;
+        const uint32_t lbo = 128, sbo = (ROWS / 8) * 128;             // K groups adjacent, MN groups 512 B apart
         for (int st = 0; st < n_stages; ++st) {
             const int s = st % STAGES;
             const bool first = (st % DRAIN_STAGES) == 0;              // first stage after a drain: overwrite
@@ -291,33 +313,38 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t pbase = smem_u32(sP + s * stage_bytes);
-                const uint32_t lbo = 128, sbo = (ROWS / 8) * 128;     // K groups adjacent, MN groups 1024 B apart
-                uint32_t used = 0;                                    // bit (mb*7+s): accumulator already written
-#pragma unroll 1
-                for (int ks = 0; ks < ROWS / 32; ++ks) {
-                    const uint32_t koff = ks * 4 * 128;               // 32 K rows = 4 groups of 8
-                    for (int mb = 0; mb < n_mb; ++mb) {
-#pragma unroll 1
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t ad = make_desc(pbase + k * plane_bytes + (mb * 8) * sbo + koff, lbo, sbo);
-#pragma unroll 1
-                            for (int l = 0; l < 4; ++l) {
-                                const uint64_t bd = make_desc(pbase + l * plane_bytes + (js * 2) * sbo + koff, lbo, sbo);
-                                const int g = k + l;
-                                const uint32_t bit = 1u << (mb * GROUPS + g);
-                                const uint32_t acc = (first && !(used & bit)) ? 0u : 1u;
-                                used |= bit;
-                                mma_i8(tmem_base + (uint32_t)((mb * GROUPS + g) * STRIPE), ad, bd, make_idesc_i8(k == 3, l == 3), acc);
-                            }
+                uint32_t used = 0;                                    // bit (mb*7+g): accumulator already written
+                for (int mb = 0; mb < n_mb; ++mb) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t ad = make_desc(pbase + k * plane_bytes + (mb * 8) * sbo, lbo, sbo);
+#pragma unroll
+                        for (int l = 0; l < 4; ++l) {
+                            const uint64_t bd = make_desc(pbase + l * plane_bytes + (js * 2) * sbo, lbo, sbo);
+                            const int g = k + l;
+                            const uint32_t bit = 1u << (mb * GROUPS + g);
+                            const uint32_t acc = (first && !(used & bit)) ? 0u : 1u;
+                            used |= bit;
+                            mma_i8(tmem_base + (uint32_t)((mb * GROUPS + g) * STRIPE), ad, bd, make_idesc_i8(k == 3, l == 3), acc);
                         }
                     }
                 }
                 mma_commit(&empty[s]);
-                const bool last_of_window = ((st + 1) % DRAIN_STAGES) == 0 || st + 1 == n_stages;
-                if (last_of_window) mma_commit(acc_full);
+                if (((st + 1) % DRAIN_STAGES) == 0 || st + 1 == n_stages) mma_commit(acc_full);
             }
             __syncwarp();
             if (((st + 1) % DRAIN_STAGES) == 0 || st + 1 == n_stages) ++drains;
+        }
+    } else if (lane == 0) {
+        // ------------------------------------------------------------ TMA loader: one 1-D bulk copy per row
+        for (int st = 0; st < n_stages; ++st) {
+            const int s = st % STAGES;
+            mbar_wait(&raw_empty[s], ((st / STAGES) & 1) ^ 1);
+            const int64_t row0 = r0 + (int64_t)st * ROWS;
+            const int rows = (int)min((int64_t)ROWS, r1 - row0);
+            mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(rows * d * 4));
+            unsigned char *dst = sR + s * raw_bytes;
+            for (int rr = 0; rr < rows; ++rr) bulk_g2s(dst + rr * raw_stride, x + (row0 + rr) * (int64_t)d, (uint32_t)(d * 4), &raw_full[s]);
         }
     }
 
@@ -372,7 +399,7 @@ void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double 
     int64_t slices = std::max<int64_t>(1, std::min<int64_t>(148 / stripes, (n + 4 * ROWS - 1) / (4 * ROWS)));   // one wave
     const int64_t rows_per_slice = ((n + slices - 1) / slices + ROWS - 1) / ROWS * ROWS;
     slices = (n + rows_per_slice - 1) / rows_per_slice;
-    const size_t smem = (size_t)STAGES * 4 * ROWS * d + 16 * sizeof(uint64_t) + 16;
+    const size_t smem = (size_t)STAGES * (4 * ROWS * d + ROWS * (d * 4 + RAW_PAD)) + 24 * sizeof(uint64_t) + 16;
     static bool attr = false;
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
     dim3 grid((unsigned)stripes, (unsigned)slices);

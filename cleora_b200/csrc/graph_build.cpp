@@ -386,30 +386,55 @@ std::unique_ptr<Graph> build_from_pairs(const uint32_t *u, const uint32_t *v, in
     auto g = std::make_unique<Graph>();
     g->desc = Descriptor{0, 1, column_name, column_name};
     uint32_t max_id = 0;
+    #pragma omp parallel for reduction(max : max_id) schedule(static)
     for (int64_t i = 0; i < n_pairs; ++i) max_id = std::max(max_id, std::max(u[i], v[i]));
-    // first-appearance relabel
-    std::vector<uint32_t> label(n_pairs ? size_t(max_id) + 1 : 0, 0xFFFFFFFFu), original;
-    for (int64_t i = 0; i < n_pairs; ++i)
-        for (uint32_t x : {u[i], v[i]})
-            if (label[x] == 0xFFFFFFFFu) { label[x] = (uint32_t)original.size(); original.push_back(x); }
+    // first-appearance relabel, in parallel: first[x] = smallest position (2i for u[i], 2i+1 for v[i]) at which x
+    // occurs; entities ordered by that position get labels 0, 1, 2, ... (identical to a sequential scan)
+    const size_t n_ids = n_pairs ? size_t(max_id) + 1 : 0;
+    constexpr uint64_t NEVER = ~0ull;
+    std::vector<uint64_t> first(n_ids, NEVER);
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t x = side ? v[i] : u[i];
+            const uint64_t pos = uint64_t(2 * i + side);
+            uint64_t cur = __atomic_load_n(&first[x], __ATOMIC_RELAXED);
+            while (pos < cur && !__atomic_compare_exchange_n(&first[x], &cur, pos, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+        }
+    }
+    std::vector<uint32_t> original;
+    original.reserve(n_ids);
+    for (size_t x = 0; x < n_ids; ++x)
+        if (first[x] != NEVER) original.push_back(uint32_t(x));
+    std::sort(original.begin(), original.end(), [&](uint32_t a, uint32_t b) { return first[a] < first[b]; });
+    std::vector<uint32_t> label(n_ids, 0xFFFFFFFFu);
     const int64_t n = (int64_t)original.size();
+    #pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n; ++k) label[original[size_t(k)]] = uint32_t(k);
+    { std::vector<uint64_t>().swap(first); }
     g->n_rows = g->n_cols = n;
-    // upper bound of entries per row, then bucket
+    // entries per row (upper bound before merging duplicates), then bucket; weights are exact multiples of 0.5, so
+    // the order in which a row's entries arrive does not change any sum
     std::vector<int64_t> start(size_t(n) + 1, 0);
+    #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n_pairs; ++i) {
         const uint32_t a = label[u[i]], b = label[v[i]];
-        if (a == b) start[a + 1] += 1; else { start[a + 1] += 2; start[b + 1] += 2; }
+        if (a == b) { __atomic_fetch_add(&start[a + 1], 1, __ATOMIC_RELAXED); }
+        else { __atomic_fetch_add(&start[a + 1], 2, __ATOMIC_RELAXED); __atomic_fetch_add(&start[b + 1], 2, __ATOMIC_RELAXED); }
     }
     std::partial_sum(start.begin(), start.end(), start.begin());
     std::vector<std::pair<uint32_t, float>> ent((size_t)start[(size_t)n]);
     {
         std::vector<int64_t> cur(start.begin(), start.end() - 1);
+        #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < n_pairs; ++i) {
             const uint32_t a = label[u[i]], b = label[v[i]];
-            if (a == b) ent[size_t(cur[a]++)] = {a, 2.0f};
+            if (a == b) ent[size_t(__atomic_fetch_add(&cur[a], 1, __ATOMIC_RELAXED))] = {a, 2.0f};
             else {
-                ent[size_t(cur[a]++)] = {a, 0.5f}; ent[size_t(cur[a]++)] = {b, 0.5f};
-                ent[size_t(cur[b]++)] = {b, 0.5f}; ent[size_t(cur[b]++)] = {a, 0.5f};
+                const int64_t pa = __atomic_fetch_add(&cur[a], 2, __ATOMIC_RELAXED);
+                ent[size_t(pa)] = {a, 0.5f}; ent[size_t(pa + 1)] = {b, 0.5f};
+                const int64_t pb = __atomic_fetch_add(&cur[b], 2, __ATOMIC_RELAXED);
+                ent[size_t(pb)] = {b, 0.5f}; ent[size_t(pb + 1)] = {a, 0.5f};
             }
         }
     }

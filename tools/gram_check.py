@@ -14,7 +14,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     L = _lib.lib()
     mode = os.environ.get("CLEORA_B200_GRAM", "i8")
     out = {}
-    for n, d in [(1_000_000, 256), (300_000, 128), (2_449_029, 256)]:
+    for n, d in [(1_000_000, 256), (300_000, 128)]:
         g = torch.Generator(device="cuda").manual_seed(n + d)
         x = torch.randn(n, d, device="cuda", generator=g) * torch.linspace(0.3, 2.0, d, device="cuda") + 0.1
         x = torch.nn.functional.normalize(x, dim=1).contiguous()
@@ -45,7 +45,7 @@ else:
             print(r.stdout[-2500:], r.stderr[-2500:], flush=True)
         except subprocess.TimeoutExpired as e:
             print(f"[{mode}] TIMEOUT", (e.stdout or b"")[-2000:], flush=True)
-    for n, d in [(1_000_000, 256), (300_000, 128), (2_449_029, 256)]:
+    for n, d in [(1_000_000, 256), (300_000, 128)]:
         try:
             a, b = np.load(f"/tmp/gram_i8_{n}_{d}.npy"), np.load(f"/tmp/gram_v3_{n}_{d}.npy")
             print(f"i8 vs DMMA n={n} d={d}: max|diff|/max|cov| = {np.max(np.abs(a - b)) / np.max(np.abs(b)):.3e}", flush=True)
