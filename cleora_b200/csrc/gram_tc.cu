@@ -29,11 +29,11 @@ namespace g8 {
 
 constexpr int ROWS = 32;           // rows (K) per stage = one MMA k-step
 constexpr int STAGES = 3;
-constexpr int RAW_PAD = 16;        // raw f32 rows are staged with a 16-byte skew: conflict-free LDS.128 across rows
-constexpr int STRIPE = 32;         // output columns per CTA (UMMA N)
+constexpr int STRIPE = 64;         // output columns per CTA (UMMA N); the CTA owns ONE 128-row block i x this stripe
 constexpr int GROUPS = 7;          // weight groups s = k + l
 constexpr int DRAIN_STAGES = 192;  // 192*32 = 6144 rows: 4 * 255^2 * 6144 < 2^31
-constexpr int THREADS = 320;
+constexpr int CONV_THREADS = 256;  // 8 converter warps
+constexpr int THREADS = CONV_THREADS + 128 + 64;   // + 4 drain warps + MMA warp + TMA warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -163,35 +163,39 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int plane_bytes = ROWS * d;                                 // one byte plane of one stage
     const int stage_bytes = 4 * plane_bytes;
-    const int raw_stride = d * 4 + RAW_PAD;                           // bytes per staged f32 row
+    const int raw_stride = d * 4;                                     // bytes per staged f32 row (dense)
     const int raw_bytes = ROWS * raw_stride;
     unsigned char *sP = smem_raw;                                     // [STAGES] byte planes (MMA operands)
     unsigned char *sR = sP + STAGES * stage_bytes;                    // [STAGES] raw f32 rows (TMA destination)
     uint64_t *bars = reinterpret_cast<uint64_t *>(sR + STAGES * raw_bytes);
     uint64_t *raw_full = bars;                   // [STAGES] count 1 + tx bytes (TMA)
-    uint64_t *raw_empty = bars + STAGES;         // [STAGES] count 128 (converters)
-    uint64_t *full = bars + 2 * STAGES;          // [STAGES] count 128 (converters): planes ready
+    uint64_t *raw_empty = bars + STAGES;         // [STAGES] count CONV_THREADS
+    uint64_t *full = bars + 2 * STAGES;          // [STAGES] count CONV_THREADS: planes ready
     uint64_t *empty = bars + 3 * STAGES;         // [STAGES] count 1 (tcgen05.commit): planes consumed
     uint64_t *acc_full = bars + 4 * STAGES;      // count 1
     uint64_t *acc_empty = acc_full + 1;          // count 128 (drain threads)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int js = blockIdx.x;                                        // output column stripe
+    const int n_mb = d / 128;
+    const int mb = blockIdx.x % n_mb;                                 // output row block i (128 columns of x)
+    const int js = blockIdx.x / n_mb;                                 // output column stripe j (64 columns of x)
+    const bool owns_colsum = blockIdx.x == 0;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice, r1 = min(n, r0 + rows_per_slice);
     const int n_stages = (int)((r1 - r0 + ROWS - 1) / ROWS);
-    const int n_mb = d / 128;
     const int n_cg = d / 16;                                          // 16-byte column groups per row
+    constexpr int CONV_WARPS = CONV_THREADS / 32;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); mbar_init(&full[s], 128); mbar_init(&empty[s], 1);
+            mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], CONV_THREADS);
+            mbar_init(&full[s], CONV_THREADS); mbar_init(&empty[s], 1);
         }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == CONV_WARPS + 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -200,18 +204,21 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < CONV_WARPS) {
         // ------------------------------------------------------------ converters: raw f32 (smem) -> 4 byte planes
-        // thread -> (row lane rl = tid % 8, column group cs = tid / 8); rows rl + 8*i of the stage.  A quarter-warp =
-        // 8 rows of one column group = one 128-byte core matrix (conflict-free STS.128); the raw rows are skewed by 16
-        // bytes so the 8 LDS.128 of a quarter-warp hit distinct banks as well.
-        const int rl = threadIdx.x & 7, cs = threadIdx.x >> 3;
+        // thread -> (row lane rl = tid % 8, slot cs = (tid / 8) % 16, half h = tid / 128); it converts rows rl + 8*i,
+        // i in {2h, 2h+1}, of column group cg = (cs + rl/4) mod n_cg, reading the row's four 16-byte pieces in the
+        // rotated order (q + rl) mod 4.  With that skew the 8 lanes of a quarter-warp touch 8 distinct 16-byte bank
+        // slots on the dense raw tile (LDS.128) and 8 consecutive rows of one or two core matrices on the plane side
+        // (STS.128): both conflict-free.
+        const int rl = threadIdx.x & 7, cs = (threadIdx.x >> 3) & 15, half = threadIdx.x >> 7;
         const bool has_cg = cs < n_cg;
+        const int cg = has_cg ? (cs + (rl >> 2)) % n_cg : 0;
         const float scale = qp->scale;
         int4 mi[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) mi[q] = has_cg ? __ldg(reinterpret_cast<const int4 *>(m_int + cs * 16) + q) : make_int4(0, 0, 0, 0);
-        long long csum[16];                              // exact column sums of q for this thread's column group
+        for (int q = 0; q < 4; ++q) mi[q] = __ldg(reinterpret_cast<const int4 *>(m_int + cg * 16) + q);
+        long long csum[16];                              // exact column sums of q over this thread's rows
 #pragma unroll
         for (int c = 0; c < 16; ++c) csum[c] = 0;
         for (int st = 0; st < n_stages; ++st) {
@@ -223,25 +230,28 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             unsigned char *base = sP + s * stage_bytes;
             if (has_cg) {
 #pragma unroll
-                for (int i = 0; i < ROWS / 8; ++i) {
-                    const int rr = rl + 8 * i;
+                for (int ii = 0; ii < 2; ++ii) {
+                    const int rr = rl + 8 * (2 * half + ii);
                     const int64_t row = r0 + (int64_t)st * ROWS + rr;
                     int qv[16];
                     if (row < r1) {
-                        const float4 *xp = reinterpret_cast<const float4 *>(raw + rr * raw_stride + cs * 64);
+                        const float4 *xp = reinterpret_cast<const float4 *>(raw + rr * raw_stride + cg * 64);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const int q = (qq + rl) & 3;                 // rotated piece order (bank skew)
                             const float4 v = xp[q];
-                            qv[4 * q + 0] = __float2int_rn(v.x * scale) - mi[q].x;
-                            qv[4 * q + 1] = __float2int_rn(v.y * scale) - mi[q].y;
-                            qv[4 * q + 2] = __float2int_rn(v.z * scale) - mi[q].z;
-                            qv[4 * q + 3] = __float2int_rn(v.w * scale) - mi[q].w;
+                            const int4 m4 = q == 0 ? mi[0] : q == 1 ? mi[1] : q == 2 ? mi[2] : mi[3];
+                            const int a0 = __float2int_rn(v.x * scale) - m4.x, a1 = __float2int_rn(v.y * scale) - m4.y;
+                            const int a2 = __float2int_rn(v.z * scale) - m4.z, a3 = __float2int_rn(v.w * scale) - m4.w;
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)                   // static register indices: select by t == q
+                                if (t == q) { qv[4 * t] = a0; qv[4 * t + 1] = a1; qv[4 * t + 2] = a2; qv[4 * t + 3] = a3; }
                         }
                     } else {
 #pragma unroll
                         for (int c = 0; c < 16; ++c) qv[c] = 0;
                     }
-                    const uint32_t off = (uint32_t)((rr & 7) * 16 + (rr >> 3) * 128 + cs * (ROWS / 8) * 128);
+                    const uint32_t off = (uint32_t)((rr & 7) * 16 + (rr >> 3) * 128 + cg * (ROWS / 8) * 128);
 #pragma unroll
                     for (int p = 0; p < 4; ++p) {        // word w of plane p = byte p of qv[4w .. 4w+3]
                         uint4 o;
@@ -254,7 +264,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
                         }
                         *reinterpret_cast<uint4 *>(base + p * plane_bytes + off) = o;
                     }
-                    if (js == 0) {
+                    if (owns_colsum) {
 #pragma unroll
                         for (int c = 0; c < 16; ++c) csum[c] += qv[c];
                     }
@@ -264,31 +274,25 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             mbar_arrive(&full[s]);
             mbar_arrive(&raw_empty[s]);
         }
-        if (js == 0) {                                      // stripe 0 owns the column sums: 8 row lanes -> 1
+        if (owns_colsum && has_cg) {                    // integer atomics: exact and order-independent
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                long long v = csum[c];
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                if (rl == 0 && has_cg && v != 0)
-                    atomicAdd(reinterpret_cast<unsigned long long *>(colsum + cs * 16 + c), (unsigned long long)v);
-            }
+            for (int c = 0; c < 16; ++c)
+                if (csum[c] != 0) atomicAdd(reinterpret_cast<unsigned long long *>(colsum + cg * 16 + c), (unsigned long long)csum[c]);
         }
-    } else if (warp < 8) {
+    } else if (warp < CONV_WARPS + 4) {
         // ------------------------------------------------------------ drain: TMEM int32 -> global int64 (atomic)
-        const int q4 = warp - 4;
+        const int q4 = warp - CONV_WARPS;
         uint32_t v[32];
         int drains = 0;
         for (int st0 = 0; st0 < n_stages; st0 += DRAIN_STAGES, ++drains) {
             mbar_wait(acc_full, drains & 1);
             tc_fence_after();
-            for (int mb = 0; mb < n_mb; ++mb)
-                for (int s = 0; s < GROUPS; ++s) {
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((mb * GROUPS + s) * STRIPE);
+            for (int s = 0; s < GROUPS; ++s)
+                for (int h = 0; h < STRIPE / 32; ++h) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * STRIPE + h * 32);
                     tmem_ld32(taddr, v);
                     const int i = mb * 128 + q4 * 32 + lane;
-                    long long *dst = G + ((int64_t)s * d + i) * d + js * STRIPE;
+                    long long *dst = G + ((int64_t)s * d + i) * d + js * STRIPE + h * 32;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const long long val = (long long)(int32_t)v[c];
@@ -298,7 +302,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             tc_fence_before();
             mbar_arrive(acc_empty);
         }
-    } else if (warp == 8) {
+    } else if (warp == CONV_WARPS + 4) {
         // ------------------------------------------------------------ MMA issuer
         int drains = 0;
         const uint32_t lbo = 128, sbo = (ROWS / 8) * 128;             // K groups adjacent, MN groups 512 B apart
@@ -313,20 +317,17 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t pbase = smem_u32(sP + s * stage_bytes);
-                uint32_t used = 0;                                    // bit (mb*7+g): accumulator already written
-                for (int mb = 0; mb < n_mb; ++mb) {
+                uint32_t used = 0;                                    // bit g: accumulator already written this stage
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t ad = make_desc(pbase + k * plane_bytes + (mb * 8) * sbo, lbo, sbo);
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t ad = make_desc(pbase + k * plane_bytes + (mb * 8) * sbo, lbo, sbo);
 #pragma unroll
-                        for (int l = 0; l < 4; ++l) {
-                            const uint64_t bd = make_desc(pbase + l * plane_bytes + (js * 2) * sbo, lbo, sbo);
-                            const int g = k + l;
-                            const uint32_t bit = 1u << (mb * GROUPS + g);
-                            const uint32_t acc = (first && !(used & bit)) ? 0u : 1u;
-                            used |= bit;
-                            mma_i8(tmem_base + (uint32_t)((mb * GROUPS + g) * STRIPE), ad, bd, make_idesc_i8(k == 3, l == 3), acc);
-                        }
+                    for (int l = 0; l < 4; ++l) {
+                        const uint64_t bd = make_desc(pbase + l * plane_bytes + (js * (STRIPE / 16)) * sbo, lbo, sbo);
+                        const int g = k + l;
+                        const uint32_t acc = (first && !(used & (1u << g))) ? 0u : 1u;
+                        used |= 1u << g;
+                        mma_i8(tmem_base + (uint32_t)(g * STRIPE), ad, bd, make_idesc_i8(k == 3, l == 3), acc);
                     }
                 }
                 mma_commit(&empty[s]);
@@ -336,21 +337,21 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             if (((st + 1) % DRAIN_STAGES) == 0 || st + 1 == n_stages) ++drains;
         }
     } else if (lane == 0) {
-        // ------------------------------------------------------------ TMA loader: one 1-D bulk copy per row
+        // ------------------------------------------------------------ TMA loader: the stage's rows are contiguous
         for (int st = 0; st < n_stages; ++st) {
             const int s = st % STAGES;
             mbar_wait(&raw_empty[s], ((st / STAGES) & 1) ^ 1);
             const int64_t row0 = r0 + (int64_t)st * ROWS;
             const int rows = (int)min((int64_t)ROWS, r1 - row0);
-            mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(rows * d * 4));
-            unsigned char *dst = sR + s * raw_bytes;
-            for (int rr = 0; rr < rows; ++rr) bulk_g2s(dst + rr * raw_stride, x + (row0 + rr) * (int64_t)d, (uint32_t)(d * 4), &raw_full[s]);
+            const uint32_t bytes = (uint32_t)(rows * d * 4);
+            mbar_arrive_expect_tx(&raw_full[s], bytes);
+            bulk_g2s(sR + s * raw_bytes, x + row0 * (int64_t)d, bytes, &raw_full[s]);
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == CONV_WARPS + 4) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
@@ -395,11 +396,11 @@ void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double 
     LAUNCH_CHECK();
     quant_params_kernel<<<1, 256, 0, st>>>(absmax, nb, mean, (int)d, qp, m_int);
     LAUNCH_CHECK();
-    const int stripes = (int)(d / STRIPE);
+    const int stripes = (int)(d / STRIPE) * (int)(d / 128);          // tiles: (128-row block i) x (64-column stripe j)
     int64_t slices = std::max<int64_t>(1, std::min<int64_t>(148 / stripes, (n + 4 * ROWS - 1) / (4 * ROWS)));   // one wave
     const int64_t rows_per_slice = ((n + slices - 1) / slices + ROWS - 1) / ROWS * ROWS;
     slices = (n + rows_per_slice - 1) / rows_per_slice;
-    const size_t smem = (size_t)STAGES * (4 * ROWS * d + ROWS * (d * 4 + RAW_PAD)) + 24 * sizeof(uint64_t) + 16;
+    const size_t smem = (size_t)STAGES * (4 * ROWS * d + ROWS * d * 4) + 24 * sizeof(uint64_t) + 16;
     static bool attr = false;
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
     dim3 grid((unsigned)stripes, (unsigned)slices);
