@@ -29,6 +29,7 @@ namespace g8 {
 
 constexpr int ROWS = 32;           // rows (K) per stage = one MMA k-step
 constexpr int STAGES = 3;
+constexpr int RAW_PAD = 16;        // raw f32 rows are staged with a 16-byte skew: conflict-free LDS.128 across rows
 constexpr int STRIPE = 64;         // output columns per CTA (UMMA N); the CTA owns ONE 128-row block i x this stripe
 constexpr int GROUPS = 7;          // weight groups s = k + l
 constexpr int DRAIN_STAGES = 192;  // 192*32 = 6144 rows: 4 * 255^2 * 6144 < 2^31
@@ -163,7 +164,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int plane_bytes = ROWS * d;                                 // one byte plane of one stage
     const int stage_bytes = 4 * plane_bytes;
-    const int raw_stride = d * 4;                                     // bytes per staged f32 row (dense)
+    const int raw_stride = d * 4 + RAW_PAD;                           // bytes per staged f32 row (skewed)
     const int raw_bytes = ROWS * raw_stride;
     unsigned char *sP = smem_raw;                                     // [STAGES] byte planes (MMA operands)
     unsigned char *sR = sP + STAGES * stage_bytes;                    // [STAGES] raw f32 rows (TMA destination)
@@ -206,14 +207,13 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
 
     if (warp < CONV_WARPS) {
         // ------------------------------------------------------------ converters: raw f32 (smem) -> 4 byte planes
-        // thread -> (row lane rl = tid % 8, slot cs = (tid / 8) % 16, half h = tid / 128); it converts rows rl + 8*i,
-        // i in {2h, 2h+1}, of column group cg = (cs + rl/4) mod n_cg, reading the row's four 16-byte pieces in the
-        // rotated order (q + rl) mod 4.  With that skew the 8 lanes of a quarter-warp touch 8 distinct 16-byte bank
-        // slots on the dense raw tile (LDS.128) and 8 consecutive rows of one or two core matrices on the plane side
-        // (STS.128): both conflict-free.
+        // thread -> (row lane rl = tid % 8, column group cg = (tid / 8) % 16, half h = tid / 128); it converts rows
+        // rl + 8*i, i in {2h, 2h+1}.  A quarter-warp = 8 consecutive rows of one column group = one 128-byte core matrix
+        // on the plane side (conflict-free STS.128); on the raw side the 16-byte row skew puts the 8 rows in 8 distinct
+        // 16-byte bank slots (conflict-free LDS.128).
         const int rl = threadIdx.x & 7, cs = (threadIdx.x >> 3) & 15, half = threadIdx.x >> 7;
         const bool has_cg = cs < n_cg;
-        const int cg = has_cg ? (cs + (rl >> 2)) % n_cg : 0;
+        const int cg = has_cg ? cs : 0;
         const float scale = qp->scale;
         int4 mi[4];
 #pragma unroll
@@ -237,33 +237,33 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
                     if (row < r1) {
                         const float4 *xp = reinterpret_cast<const float4 *>(raw + rr * raw_stride + cg * 64);
 #pragma unroll
-                        for (int qq = 0; qq < 4; ++qq) {
-                            const int q = (qq + rl) & 3;                 // rotated piece order (bank skew)
+                        for (int q = 0; q < 4; ++q) {
                             const float4 v = xp[q];
-                            const int4 m4 = q == 0 ? mi[0] : q == 1 ? mi[1] : q == 2 ? mi[2] : mi[3];
-                            const int a0 = __float2int_rn(v.x * scale) - m4.x, a1 = __float2int_rn(v.y * scale) - m4.y;
-                            const int a2 = __float2int_rn(v.z * scale) - m4.z, a3 = __float2int_rn(v.w * scale) - m4.w;
-#pragma unroll
-                            for (int t = 0; t < 4; ++t)                   // static register indices: select by t == q
-                                if (t == q) { qv[4 * t] = a0; qv[4 * t + 1] = a1; qv[4 * t + 2] = a2; qv[4 * t + 3] = a3; }
+                            qv[4 * q + 0] = __float2int_rn(v.x * scale) - mi[q].x;
+                            qv[4 * q + 1] = __float2int_rn(v.y * scale) - mi[q].y;
+                            qv[4 * q + 2] = __float2int_rn(v.z * scale) - mi[q].z;
+                            qv[4 * q + 3] = __float2int_rn(v.w * scale) - mi[q].w;
                         }
                     } else {
 #pragma unroll
                         for (int c = 0; c < 16; ++c) qv[c] = 0;
                     }
                     const uint32_t off = (uint32_t)((rr & 7) * 16 + (rr >> 3) * 128 + cg * (ROWS / 8) * 128);
+                    // 4x4 byte transposes: word w of plane p = byte p of qv[4w .. 4w+3]  (8 PRMT per 4 values)
+                    uint4 pl[4];
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {        // word w of plane p = byte p of qv[4w .. 4w+3]
-                        uint4 o;
-                        uint32_t *ow = &o.x;
-#pragma unroll
-                        for (int wq = 0; wq < 4; ++wq) {
-                            const uint32_t lo = __byte_perm((uint32_t)qv[4 * wq], (uint32_t)qv[4 * wq + 1], 0x0040 + 0x0011 * p);
-                            const uint32_t hi = __byte_perm((uint32_t)qv[4 * wq + 2], (uint32_t)qv[4 * wq + 3], 0x0040 + 0x0011 * p);
-                            ow[wq] = __byte_perm(lo, hi, 0x5410);
-                        }
-                        *reinterpret_cast<uint4 *>(base + p * plane_bytes + off) = o;
+                    for (int wq = 0; wq < 4; ++wq) {
+                        const uint32_t a = (uint32_t)qv[4 * wq], b2 = (uint32_t)qv[4 * wq + 1];
+                        const uint32_t c2 = (uint32_t)qv[4 * wq + 2], d2 = (uint32_t)qv[4 * wq + 3];
+                        const uint32_t t0 = __byte_perm(a, b2, 0x5140), t1 = __byte_perm(a, b2, 0x7362);   // a0 b0 a1 b1 | a2 b2 a3 b3
+                        const uint32_t t2 = __byte_perm(c2, d2, 0x5140), t3 = __byte_perm(c2, d2, 0x7362);
+                        (&pl[0].x)[wq] = __byte_perm(t0, t2, 0x5410);      // a0 b0 c0 d0
+                        (&pl[1].x)[wq] = __byte_perm(t0, t2, 0x7632);      // a1 b1 c1 d1
+                        (&pl[2].x)[wq] = __byte_perm(t1, t3, 0x5410);
+                        (&pl[3].x)[wq] = __byte_perm(t1, t3, 0x7632);
                     }
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) *reinterpret_cast<uint4 *>(base + p * plane_bytes + off) = pl[p];
                     if (owns_colsum) {
 #pragma unroll
                         for (int c = 0; c < 16; ++c) csum[c] += qv[c];
@@ -337,15 +337,15 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             if (((st + 1) % DRAIN_STAGES) == 0 || st + 1 == n_stages) ++drains;
         }
     } else if (lane == 0) {
-        // ------------------------------------------------------------ TMA loader: the stage's rows are contiguous
+        // ------------------------------------------------------------ TMA loader: one 1-D bulk copy per (skewed) row
         for (int st = 0; st < n_stages; ++st) {
             const int s = st % STAGES;
             mbar_wait(&raw_empty[s], ((st / STAGES) & 1) ^ 1);
             const int64_t row0 = r0 + (int64_t)st * ROWS;
             const int rows = (int)min((int64_t)ROWS, r1 - row0);
-            const uint32_t bytes = (uint32_t)(rows * d * 4);
-            mbar_arrive_expect_tx(&raw_full[s], bytes);
-            bulk_g2s(sR + s * raw_bytes, x + row0 * (int64_t)d, bytes, &raw_full[s]);
+            mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(rows * d * 4));
+            unsigned char *dst = sR + s * raw_bytes;
+            for (int rr = 0; rr < rows; ++rr) bulk_g2s(dst + rr * raw_stride, x + (row0 + rr) * (int64_t)d, (uint32_t)(d * 4), &raw_full[s]);
         }
     }
 
@@ -400,7 +400,7 @@ void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double 
     int64_t slices = std::max<int64_t>(1, std::min<int64_t>(148 / stripes, (n + 4 * ROWS - 1) / (4 * ROWS)));   // one wave
     const int64_t rows_per_slice = ((n + slices - 1) / slices + ROWS - 1) / ROWS * ROWS;
     slices = (n + rows_per_slice - 1) / rows_per_slice;
-    const size_t smem = (size_t)STAGES * (4 * ROWS * d + ROWS * d * 4) + 24 * sizeof(uint64_t) + 16;
+    const size_t smem = (size_t)STAGES * (4 * ROWS * d + ROWS * (d * 4 + RAW_PAD)) + 24 * sizeof(uint64_t) + 16;
     static bool attr = false;
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
     dim3 grid((unsigned)stripes, (unsigned)slices);
