@@ -23,12 +23,13 @@
 #include "../../include/cleora_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace cleora {
 namespace g8 {
 
 constexpr int ROWS = 32;           // rows (K) per stage = one MMA k-step
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 6;        // barrier slots; the actual raw / plane stage counts are launch parameters
 constexpr int RAW_PAD = 16;        // raw f32 rows are staged with a 16-byte skew: conflict-free LDS.128 across rows
 constexpr int STRIPE = 64;         // output columns per CTA (UMMA N); the CTA owns ONE 128-row block i x this stripe
 constexpr int GROUPS = 7;          // weight groups s = k + l
@@ -167,7 +168,8 @@ __global__ void quant_params_kernel(const float *__restrict__ absmax_partial, in
 __global__ void __launch_bounds__(g8::THREADS, 1)
 gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantParams *__restrict__ qp,
                const int32_t *__restrict__ m_int, long long *__restrict__ G /* [7][d][d] */,
-               long long *__restrict__ colsum /* [d] */, int64_t rows_per_slice) {
+               long long *__restrict__ colsum /* [d] */, int64_t rows_per_slice, int RS /* raw stages */,
+               int PS /* plane stages */) {
     using namespace g8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int plane_bytes = ROWS * d;                                 // one byte plane of one stage
@@ -175,13 +177,13 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     const int raw_stride = d * 4 + RAW_PAD;                           // bytes per staged f32 row (skewed)
     const int raw_bytes = ROWS * raw_stride;
     unsigned char *sP = smem_raw;                                     // [STAGES] byte planes (MMA operands)
-    unsigned char *sR = sP + STAGES * stage_bytes;                    // [STAGES] raw f32 rows (TMA destination)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sR + STAGES * raw_bytes);
-    uint64_t *raw_full = bars;                   // [STAGES] count 1 + tx bytes (TMA)
-    uint64_t *raw_empty = bars + STAGES;         // [STAGES] count CONV_THREADS
-    uint64_t *full = bars + 2 * STAGES;          // [STAGES] count CONV_THREADS: planes ready
-    uint64_t *empty = bars + 3 * STAGES;         // [STAGES] count 1 (tcgen05.commit): planes consumed
-    uint64_t *acc_full = bars + 4 * STAGES;      // count 1
+    unsigned char *sR = sP + PS * stage_bytes;                        // [RS] raw f32 rows (TMA destination)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sR + RS * raw_bytes);
+    uint64_t *raw_full = bars;                   // [RS] count 1 + tx bytes (TMA)
+    uint64_t *raw_empty = bars + MAX_STAGES;     // [RS] count CONV_THREADS
+    uint64_t *full = bars + 2 * MAX_STAGES;      // [PS] count CONV_THREADS: planes ready
+    uint64_t *empty = bars + 3 * MAX_STAGES;     // [PS] count 1 (tcgen05.commit): planes consumed
+    uint64_t *acc_full = bars + 4 * MAX_STAGES;  // count 1
     uint64_t *acc_empty = acc_full + 1;          // count 128 (drain threads)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
 
@@ -196,7 +198,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     constexpr int CONV_WARPS = CONV_THREADS / 32;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
             mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], CONV_THREADS);
             mbar_init(&full[s], CONV_THREADS); mbar_init(&empty[s], 1);
         }
@@ -230,11 +232,10 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
 #pragma unroll
         for (int c = 0; c < 16; ++c) csum[c] = 0;
         for (int st = 0; st < n_stages; ++st) {
-            const int s = st % STAGES;
-            const uint32_t ph = (st / STAGES) & 1;
-            mbar_wait(&raw_full[s], ph);                 // TMA has landed this stage's rows
-            mbar_wait(&empty[s], ph ^ 1);                // the MMAs that read these planes last time have retired
-            const unsigned char *raw = sR + s * raw_bytes;
+            const int rs = st % RS, s = st % PS;
+            mbar_wait(&raw_full[rs], (st / RS) & 1);     // TMA has landed this stage's rows
+            mbar_wait(&empty[s], ((st / PS) & 1) ^ 1);   // the MMAs that read these planes last time have retired
+            const unsigned char *raw = sR + rs * raw_bytes;
             unsigned char *base = sP + s * stage_bytes;
             if (has_cg) {
 #pragma unroll
@@ -280,7 +281,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             }
             fence_proxy_async();
             mbar_arrive(&full[s]);
-            mbar_arrive(&raw_empty[s]);
+            mbar_arrive(&raw_empty[rs]);
         }
         if (owns_colsum && has_cg) {                    // integer atomics: exact and order-independent
 #pragma unroll
@@ -315,13 +316,13 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
         int drains = 0;
         const uint32_t lbo = 128, sbo = (ROWS / 8) * 128;             // K groups adjacent, MN groups 512 B apart
         for (int st = 0; st < n_stages; ++st) {
-            const int s = st % STAGES;
+            const int s = st % PS;
             const bool first = (st % DRAIN_STAGES) == 0;              // first stage after a drain: overwrite
             if (first && st > 0) {                                    // wait until the previous accumulators are drained
                 mbar_wait(acc_empty, (drains - 1) & 1, 200);
                 tc_fence_after();
             }
-            mbar_wait(&full[s], (st / STAGES) & 1);
+            mbar_wait(&full[s], (st / PS) & 1);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t pbase = smem_u32(sP + s * stage_bytes);
@@ -347,8 +348,8 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     } else if (lane == 0) {
         // ------------------------------------------------------------ TMA loader: one 1-D bulk copy per (skewed) row
         for (int st = 0; st < n_stages; ++st) {
-            const int s = st % STAGES;
-            mbar_wait(&raw_empty[s], ((st / STAGES) & 1) ^ 1);
+            const int s = st % RS;
+            mbar_wait(&raw_empty[s], ((st / RS) & 1) ^ 1);
             const int64_t row0 = r0 + (int64_t)st * ROWS;
             const int rows = (int)min((int64_t)ROWS, r1 - row0);
             mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(rows * d * 4));
@@ -408,11 +409,14 @@ void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double 
     int64_t slices = std::max<int64_t>(1, std::min<int64_t>(148 / stripes, (n + 4 * ROWS - 1) / (4 * ROWS)));   // one wave
     const int64_t rows_per_slice = ((n + slices - 1) / slices + ROWS - 1) / ROWS * ROWS;
     slices = (n + rows_per_slice - 1) / rows_per_slice;
-    const size_t smem = (size_t)STAGES * (4 * ROWS * d + ROWS * (d * 4 + RAW_PAD)) + 24 * sizeof(uint64_t) + 16;
+    static const int RS = [] { const char *e = getenv("CLEORA_B200_I8_RAW_STAGES"); return e ? atoi(e) : 4; }();
+    static const int PS = [] { const char *e = getenv("CLEORA_B200_I8_PLANE_STAGES"); return e ? atoi(e) : 2; }();
+    const size_t smem = (size_t)PS * 4 * ROWS * d + (size_t)RS * ROWS * (d * 4 + RAW_PAD) + (4 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
+    if (smem > 227 * 1024 || RS > MAX_STAGES || PS > MAX_STAGES || RS < 1 || PS < 1) throw CudaFail{"int8 Gram: stage configuration does not fit"};
     static bool attr = false;
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
     dim3 grid((unsigned)stripes, (unsigned)slices);
-    gram_i8_kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, qp, m_int, G, colsum, rows_per_slice);
+    gram_i8_kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, qp, m_int, G, colsum, rows_per_slice, RS, PS);
     LAUNCH_CHECK();
     gram_i8_combine_kernel<<<(unsigned)((d * d + 255) / 256), 256, 0, st>>>(G, colsum, m_int, mean, (int)d, n, qp, cov);
     LAUNCH_CHECK();
