@@ -35,7 +35,8 @@ constexpr int STRIPE = 64;         // output columns per CTA (UMMA N); the CTA o
 constexpr int GROUPS = 7;          // weight groups s = k + l
 constexpr int DRAIN_STAGES = 192;  // 192*32 = 6144 rows: 4 * 255^2 * 6144 < 2^31
 constexpr int CONV_THREADS = 256;  // 8 converter warps
-constexpr int THREADS = CONV_THREADS + 128 + 64;   // + 4 drain warps + MMA warp + TMA warp
+constexpr int THREADS = CONV_THREADS + 128 + 32;   // + 4 drain warps + MMA warp
+constexpr int RAW_STAGES = 4;      // per-thread cp.async ring (each thread stages exactly the 64-byte pieces it converts)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -74,6 +75,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 16-byte LDGSTS (cp.async): measured far faster than UBLKCP (cp.async.bulk) for this access pattern -- the 1-D bulk
+// engine delivered only ~8 B/clk per SM here, which capped the kernel at 4.1 ms regardless of pipeline depth.
+__device__ __forceinline__ void cp_async_ca16(void *dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -168,8 +177,7 @@ __global__ void quant_params_kernel(const float *__restrict__ absmax_partial, in
 __global__ void __launch_bounds__(g8::THREADS, 1)
 gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantParams *__restrict__ qp,
                const int32_t *__restrict__ m_int, long long *__restrict__ G /* [7][d][d] */,
-               long long *__restrict__ colsum /* [d] */, int64_t rows_per_slice, int RS /* raw stages */,
-               int PS /* plane stages */) {
+               long long *__restrict__ colsum /* [d] */, int64_t rows_per_slice, int PS /* plane stages */) {
     using namespace g8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int plane_bytes = ROWS * d;                                 // one byte plane of one stage
@@ -177,10 +185,8 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     const int raw_stride = d * 4 + RAW_PAD;                           // bytes per staged f32 row (skewed)
     const int raw_bytes = ROWS * raw_stride;
     unsigned char *sP = smem_raw;                                     // [STAGES] byte planes (MMA operands)
-    unsigned char *sR = sP + PS * stage_bytes;                        // [RS] raw f32 rows (TMA destination)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sR + RS * raw_bytes);
-    uint64_t *raw_full = bars;                   // [RS] count 1 + tx bytes (TMA)
-    uint64_t *raw_empty = bars + MAX_STAGES;     // [RS] count CONV_THREADS
+    unsigned char *sR = sP + PS * stage_bytes;                        // [RAW_STAGES] raw f32 rows (cp.async ring)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sR + RAW_STAGES * raw_bytes);
     uint64_t *full = bars + 2 * MAX_STAGES;      // [PS] count CONV_THREADS: planes ready
     uint64_t *empty = bars + 3 * MAX_STAGES;     // [PS] count 1 (tcgen05.commit): planes consumed
     uint64_t *acc_full = bars + 4 * MAX_STAGES;  // count 1
@@ -198,10 +204,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     constexpr int CONV_WARPS = CONV_THREADS / 32;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < MAX_STAGES; ++s) {
-            mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], CONV_THREADS);
-            mbar_init(&full[s], CONV_THREADS); mbar_init(&empty[s], 1);
-        }
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full[s], CONV_THREADS); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -231,9 +234,29 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
         long long csum[16];                              // exact column sums of q over this thread's rows
 #pragma unroll
         for (int c = 0; c < 16; ++c) csum[c] = 0;
+        // each thread stages (cp.async) exactly the pieces it will convert itself, RAW_STAGES - 1 stages ahead: no
+        // cross-thread hand-off is needed for the raw data, only cp.async.wait_group
+        auto issue = [&](int st) {
+            if (st < n_stages && has_cg) {
+                unsigned char *raw = sR + (st % RAW_STAGES) * raw_bytes;
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) {
+                    const int rr = rl + 8 * (2 * half + ii);
+                    const int64_t row = r0 + (int64_t)st * ROWS + rr;
+                    const bool in = row < r1;
+                    const float *src = x + (in ? row : 0) * (int64_t)d + cg * 16;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cp_async_ca16(raw + rr * raw_stride + cg * 64 + q * 16, src + q * 4, in ? 16 : 0);
+                }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int st = 0; st < RAW_STAGES - 1; ++st) issue(st);
         for (int st = 0; st < n_stages; ++st) {
-            const int rs = st % RS, s = st % PS;
-            mbar_wait(&raw_full[rs], (st / RS) & 1);     // TMA has landed this stage's rows
+            const int rs = st % RAW_STAGES, s = st % PS;
+            cp_async_wait<RAW_STAGES - 2>();             // this thread's pieces of stage st have landed
+            issue(st + RAW_STAGES - 1);                  // refill the slot this thread finished reading last trip
             mbar_wait(&empty[s], ((st / PS) & 1) ^ 1);   // the MMAs that read these planes last time have retired
             const unsigned char *raw = sR + rs * raw_bytes;
             unsigned char *base = sP + s * stage_bytes;
@@ -281,7 +304,6 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             }
             fence_proxy_async();
             mbar_arrive(&full[s]);
-            mbar_arrive(&raw_empty[rs]);
         }
         if (owns_colsum && has_cg) {                    // integer atomics: exact and order-independent
 #pragma unroll
@@ -345,17 +367,6 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             __syncwarp();
             if (((st + 1) % DRAIN_STAGES) == 0 || st + 1 == n_stages) ++drains;
         }
-    } else if (lane == 0) {
-        // ------------------------------------------------------------ TMA loader: one 1-D bulk copy per (skewed) row
-        for (int st = 0; st < n_stages; ++st) {
-            const int s = st % RS;
-            mbar_wait(&raw_empty[s], ((st / RS) & 1) ^ 1);
-            const int64_t row0 = r0 + (int64_t)st * ROWS;
-            const int rows = (int)min((int64_t)ROWS, r1 - row0);
-            mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(rows * d * 4));
-            unsigned char *dst = sR + s * raw_bytes;
-            for (int rr = 0; rr < rows; ++rr) bulk_g2s(dst + rr * raw_stride, x + (row0 + rr) * (int64_t)d, (uint32_t)(d * 4), &raw_full[s]);
-        }
     }
 
     tc_fence_before();
@@ -409,14 +420,12 @@ void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double 
     int64_t slices = std::max<int64_t>(1, std::min<int64_t>(148 / stripes, (n + 4 * ROWS - 1) / (4 * ROWS)));   // one wave
     const int64_t rows_per_slice = ((n + slices - 1) / slices + ROWS - 1) / ROWS * ROWS;
     slices = (n + rows_per_slice - 1) / rows_per_slice;
-    static const int RS = [] { const char *e = getenv("CLEORA_B200_I8_RAW_STAGES"); return e ? atoi(e) : 4; }();
-    static const int PS = [] { const char *e = getenv("CLEORA_B200_I8_PLANE_STAGES"); return e ? atoi(e) : 2; }();
-    const size_t smem = (size_t)PS * 4 * ROWS * d + (size_t)RS * ROWS * (d * 4 + RAW_PAD) + (4 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
-    if (smem > 227 * 1024 || RS > MAX_STAGES || PS > MAX_STAGES || RS < 1 || PS < 1) throw CudaFail{"int8 Gram: stage configuration does not fit"};
+    const int PS = 2;
+    const size_t smem = (size_t)PS * 4 * ROWS * d + (size_t)RAW_STAGES * ROWS * (d * 4 + RAW_PAD) + (4 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
     static bool attr = false;
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
     dim3 grid((unsigned)stripes, (unsigned)slices);
-    gram_i8_kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, qp, m_int, G, colsum, rows_per_slice, RS, PS);
+    gram_i8_kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, qp, m_int, G, colsum, rows_per_slice, PS);
     LAUNCH_CHECK();
     gram_i8_combine_kernel<<<(unsigned)((d * d + 255) / 256), 256, 0, st>>>(G, colsum, m_int, mean, (int)d, n, qp, cov);
     LAUNCH_CHECK();
