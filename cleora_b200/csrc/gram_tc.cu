@@ -35,8 +35,9 @@ constexpr int STRIPE = 64;         // output columns per CTA (UMMA N); the CTA o
 constexpr int GROUPS = 7;          // weight groups s = k + l
 constexpr int DRAIN_STAGES = 192;  // 192*32 = 6144 rows: 4 * 255^2 * 6144 < 2^31
 constexpr int CONV_THREADS = 256;  // 8 converter warps
-constexpr int THREADS = CONV_THREADS + 128 + 32;   // + 4 drain warps + MMA warp
-constexpr int RAW_STAGES = 4;      // per-thread cp.async ring (each thread stages exactly the 64-byte pieces it converts)
+constexpr int LOAD_THREADS = 128;  // 4 loader warps (cp.async, fully coalesced)
+constexpr int THREADS = CONV_THREADS + 128 + 32 + LOAD_THREADS;   // + 4 drain warps + MMA warp + loaders
+constexpr int RAW_STAGES = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -77,9 +78,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 // 16-byte LDGSTS (cp.async): measured far faster than UBLKCP (cp.async.bulk) for this access pattern -- the 1-D bulk
 // engine delivered only ~8 B/clk per SM here, which capped the kernel at 4.1 ms regardless of pipeline depth.
-__device__ __forceinline__ void cp_async_ca16(void *dst, const void *src, int src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void cp_async_cg16(void *dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
+// the mbarrier gets one (pre-counted) arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -187,6 +193,8 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     unsigned char *sP = smem_raw;                                     // [STAGES] byte planes (MMA operands)
     unsigned char *sR = sP + PS * stage_bytes;                        // [RAW_STAGES] raw f32 rows (cp.async ring)
     uint64_t *bars = reinterpret_cast<uint64_t *>(sR + RAW_STAGES * raw_bytes);
+    uint64_t *raw_full = bars;                   // [RAW_STAGES] count LOAD_THREADS (cp.async noinc arrivals)
+    uint64_t *raw_empty = bars + MAX_STAGES;     // [RAW_STAGES] count CONV_THREADS
     uint64_t *full = bars + 2 * MAX_STAGES;      // [PS] count CONV_THREADS: planes ready
     uint64_t *empty = bars + 3 * MAX_STAGES;     // [PS] count 1 (tcgen05.commit): planes consumed
     uint64_t *acc_full = bars + 4 * MAX_STAGES;  // count 1
@@ -204,7 +212,10 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     constexpr int CONV_WARPS = CONV_THREADS / 32;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full[s], CONV_THREADS); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < MAX_STAGES; ++s) {
+            mbar_init(&raw_full[s], LOAD_THREADS); mbar_init(&raw_empty[s], CONV_THREADS);
+            mbar_init(&full[s], CONV_THREADS); mbar_init(&empty[s], 1);
+        }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -234,29 +245,9 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
         long long csum[16];                              // exact column sums of q over this thread's rows
 #pragma unroll
         for (int c = 0; c < 16; ++c) csum[c] = 0;
-        // each thread stages (cp.async) exactly the pieces it will convert itself, RAW_STAGES - 1 stages ahead: no
-        // cross-thread hand-off is needed for the raw data, only cp.async.wait_group
-        auto issue = [&](int st) {
-            if (st < n_stages && has_cg) {
-                unsigned char *raw = sR + (st % RAW_STAGES) * raw_bytes;
-#pragma unroll
-                for (int ii = 0; ii < 2; ++ii) {
-                    const int rr = rl + 8 * (2 * half + ii);
-                    const int64_t row = r0 + (int64_t)st * ROWS + rr;
-                    const bool in = row < r1;
-                    const float *src = x + (in ? row : 0) * (int64_t)d + cg * 16;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) cp_async_ca16(raw + rr * raw_stride + cg * 64 + q * 16, src + q * 4, in ? 16 : 0);
-                }
-            }
-            cp_async_commit();
-        };
-#pragma unroll
-        for (int st = 0; st < RAW_STAGES - 1; ++st) issue(st);
         for (int st = 0; st < n_stages; ++st) {
             const int rs = st % RAW_STAGES, s = st % PS;
-            cp_async_wait<RAW_STAGES - 2>();             // this thread's pieces of stage st have landed
-            issue(st + RAW_STAGES - 1);                  // refill the slot this thread finished reading last trip
+            mbar_wait(&raw_full[rs], (st / RAW_STAGES) & 1);   // the loaders' cp.async for this stage have landed
             mbar_wait(&empty[s], ((st / PS) & 1) ^ 1);   // the MMAs that read these planes last time have retired
             const unsigned char *raw = sR + rs * raw_bytes;
             unsigned char *base = sP + s * stage_bytes;
@@ -304,6 +295,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             }
             fence_proxy_async();
             mbar_arrive(&full[s]);
+            mbar_arrive(&raw_empty[rs]);
         }
         if (owns_colsum && has_cg) {                    // integer atomics: exact and order-independent
 #pragma unroll
@@ -367,6 +359,25 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             __syncwarp();
             if (((st + 1) % DRAIN_STAGES) == 0 || st + 1 == n_stages) ++drains;
         }
+    } else if (warp >= CONV_WARPS + 5) {
+        // ------------------------------------------------------------ loaders: coalesced 16-byte cp.async, 4 stages deep.
+        // (Separate warps on purpose: the converters' fence.proxy.async would otherwise wait for their own in-flight
+        //  prefetches and serialise the ring.)
+        const int lt = threadIdx.x - (CONV_WARPS + 5) * 32;            // 0..127
+        const int pieces_per_row = d / 4;                               // 16-byte pieces
+        for (int st = 0; st < n_stages; ++st) {
+            const int rs = st % RAW_STAGES;
+            mbar_wait(&raw_empty[rs], ((st / RAW_STAGES) & 1) ^ 1);
+            unsigned char *raw = sR + rs * raw_bytes;
+            const int64_t row0 = r0 + (int64_t)st * ROWS;
+            for (int p = lt; p < ROWS * pieces_per_row; p += LOAD_THREADS) {
+                const int rr = p / pieces_per_row, pc = p - rr * pieces_per_row;
+                const bool in = row0 + rr < r1;
+                cp_async_cg16(raw + rr * raw_stride + pc * 16, x + (in ? row0 + rr : 0) * (int64_t)d + pc * 4, in ? 16 : 0);
+            }
+            cp_async_arrive_noinc(&raw_full[rs]);
+        }
+        cp_async_wait_all();
     }
 
     tc_fence_before();

@@ -29,7 +29,8 @@ constexpr int BK = 32;             // K per stage (floats) = 128 bytes per row
 constexpr int STAGES = 2;
 constexpr int NMAX = 256;          // UMMA N limit
 constexpr int A_BYTES = BM * BK * 4;            // 16 KB (one of hi / lo)
-constexpr int THREADS = 320;
+constexpr int B_LOAD_THREADS = 64;  // 2 loader warps for the transform
+constexpr int THREADS = 288 + B_LOAD_THREADS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -69,6 +70,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 16-byte LDGSTS for the B operand: the 1-D bulk engine (cp.async.bulk / UBLKCP) sustained only ~15 B/clk per SM on
+// these 64 KB chunks and was the stage-time limiter (measured); LDGSTS from two warps is several times faster.
+__device__ __forceinline__ void cp_async_cg16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -153,7 +163,7 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
     const int64_t n_tiles = (n + BM - 1) / BM;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_a[s], 128); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_a[s], 128); mbar_init(&full_b[s], B_LOAD_THREADS); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -277,19 +287,22 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
             }
         }
     } else {
-        // ------------------------------------------------------------------ B loader (TMA 1-D bulk copies)
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int c = 0; c < n_chunks; ++c, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full_b[s], 2 * b_bytes);
-                    bulk_g2s(sB + s * 2 * b_bytes, Bt + (int64_t)c * 2 * N * BK, 2 * b_bytes, &full_b[s]);
-                }
+        // ------------------------------------------------------------------ B loaders (cp.async, 2 warps)
+        const int lt = threadIdx.x - 9 * 32;                    // 0..63
+        const int pieces = (2 * b_bytes) / 16;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int c = 0; c < n_chunks; ++c, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                unsigned char *dst = sB + s * 2 * b_bytes;
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(Bt + (int64_t)c * 2 * N * BK);
+                for (int p = lt; p < pieces; p += B_LOAD_THREADS) cp_async_cg16(dst + p * 16, src + p * 16);
+                cp_async_arrive_noinc(&full_b[s]);
             }
         }
+        cp_async_wait_all();
     }
 
     tc_fence_before();
