@@ -363,17 +363,24 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
         // ------------------------------------------------------------ loaders: coalesced 16-byte cp.async, 4 stages deep.
         // (Separate warps on purpose: the converters' fence.proxy.async would otherwise wait for their own in-flight
         //  prefetches and serialise the ring.)
+        // thread -> fixed 16-byte column piece pc and a fixed row phase; it walks down the stage's rows with constant
+        // strides (no per-piece division: the first version spent ~80 instructions per piece on index arithmetic)
         const int lt = threadIdx.x - (CONV_WARPS + 5) * 32;            // 0..127
-        const int pieces_per_row = d / 4;                               // 16-byte pieces
+        const int ppr = d / 4;                                          // 16-byte pieces per row: 32 (d=128) or 64 (d=256)
+        const int pc = lt % ppr, rr0 = lt / ppr, rstep = LOAD_THREADS / ppr;   // rows rr0, rr0+rstep, ...
         for (int st = 0; st < n_stages; ++st) {
             const int rs = st % RAW_STAGES;
             mbar_wait(&raw_empty[rs], ((st / RAW_STAGES) & 1) ^ 1);
-            unsigned char *raw = sR + rs * raw_bytes;
             const int64_t row0 = r0 + (int64_t)st * ROWS;
-            for (int p = lt; p < ROWS * pieces_per_row; p += LOAD_THREADS) {
-                const int rr = p / pieces_per_row, pc = p - rr * pieces_per_row;
-                const bool in = row0 + rr < r1;
-                cp_async_cg16(raw + rr * raw_stride + pc * 16, x + (in ? row0 + rr : 0) * (int64_t)d + pc * 4, in ? 16 : 0);
+            unsigned char *dst = sR + rs * raw_bytes + rr0 * raw_stride + pc * 16;
+            const float *src = x + (row0 + rr0) * (int64_t)d + pc * 4;
+            const int64_t rows_left = r1 - row0;                        // >= 1
+#pragma unroll 4
+            for (int rr = rr0; rr < ROWS; rr += rstep) {
+                const bool in = rr < rows_left;
+                cp_async_cg16(dst, in ? src : x, in ? 16 : 0);
+                dst += rstep * raw_stride;
+                src += (int64_t)rstep * d;
             }
             cp_async_arrive_noinc(&raw_full[rs]);
         }
