@@ -178,52 +178,38 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
 
     if (warp < 4) {
         // ------------------------------------------------------------------ A producers (thread = row of the tile)
-        // The (tile, chunk) sequence is flattened and the global loads run one step ahead of the conversion (second
-        // register set): with only the current chunk in flight the producers sat on the load latency 65 % of the time.
         const int r = threadIdx.x;                     // 0..127
-        const int off = (r & 7) * 16 + (r >> 3) * 1024;
-        const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const int64_t steps = my_tiles * n_chunks;
-        float4 v[8], nx[8];
-        float rs = 1.f, rs_nx = 1.f;
-        bool in = false, in_nx = false;
-        auto fetch = [&](int64_t step, float4 (&dst)[8], bool &in_f, float &rs_f) {
-            const int64_t tile = blockIdx.x + (step / n_chunks) * gridDim.x;
-            const int c = (int)(step % n_chunks);
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t row = tile * BM + r;
-            in_f = row < n;
-            const float4 *xr = reinterpret_cast<const float4 *>(x + (in_f ? row : 0) * (int64_t)d) + c * 8;
+            const bool in = row < n;
+            const float4 *xr = reinterpret_cast<const float4 *>(x + (in ? row : 0) * (int64_t)d);
+            const float rs = (SCALED && in) ? __ldg(rowscale + row) : 1.f;
+            for (int c = 0; c < n_chunks; ++c, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                float4 v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) dst[q] = in_f ? __ldg(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            rs_f = (SCALED && in_f) ? __ldg(rowscale + row) : 1.f;
-        };
-        if (steps > 0) fetch(0, v, in, rs);
-        for (int64_t it64 = 0; it64 < steps; ++it64) {
-            const uint32_t it = (uint32_t)it64;
-            const int c = (int)(it64 % n_chunks);
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            if (it64 + 1 < steps) fetch(it64 + 1, nx, in_nx, rs_nx);      // next step's loads are in flight from here on
-            const float4 *mp = reinterpret_cast<const float4 *>(mean + c * BK);
-            mbar_wait(&empty[s], ph ^ 1);              // stage free (first round passes immediately)
-            unsigned char *hi = sA + s * 2 * A_BYTES, *lo = hi + A_BYTES;
+                for (int q = 0; q < 8; ++q) v[q] = in ? __ldg(xr + c * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 *mp = reinterpret_cast<const float4 *>(mean + c * BK);
+                mbar_wait(&empty[s], ph ^ 1);          // stage free (first round passes immediately)
+                unsigned char *hi = sA + s * 2 * A_BYTES, *lo = hi + A_BYTES;
+                const int off = (r & 7) * 16 + (r >> 3) * 1024;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float4 m = __ldg(mp + q);
-                if (SCALED) { m.x = __fmul_rn(rs, m.x); m.y = __fmul_rn(rs, m.y); m.z = __fmul_rn(rs, m.z); m.w = __fmul_rn(rs, m.w); }
-                float4 a, h, l;
-                a.x = in ? __fsub_rn(v[q].x, m.x) : 0.f; a.y = in ? __fsub_rn(v[q].y, m.y) : 0.f;
-                a.z = in ? __fsub_rn(v[q].z, m.z) : 0.f; a.w = in ? __fsub_rn(v[q].w, m.w) : 0.f;
-                h.x = tf32_hi(a.x); h.y = tf32_hi(a.y); h.z = tf32_hi(a.z); h.w = tf32_hi(a.w);
-                l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
-                *reinterpret_cast<float4 *>(hi + off + q * 128) = h;
-                *reinterpret_cast<float4 *>(lo + off + q * 128) = l;
+                for (int q = 0; q < 8; ++q) {
+                    float4 m = __ldg(mp + q);
+                    if (SCALED) { m.x = __fmul_rn(rs, m.x); m.y = __fmul_rn(rs, m.y); m.z = __fmul_rn(rs, m.z); m.w = __fmul_rn(rs, m.w); }
+                    float4 a, h, l;
+                    a.x = in ? __fsub_rn(v[q].x, m.x) : 0.f; a.y = in ? __fsub_rn(v[q].y, m.y) : 0.f;
+                    a.z = in ? __fsub_rn(v[q].z, m.z) : 0.f; a.w = in ? __fsub_rn(v[q].w, m.w) : 0.f;
+                    h.x = tf32_hi(a.x); h.y = tf32_hi(a.y); h.z = tf32_hi(a.z); h.w = tf32_hi(a.w);
+                    l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
+                    *reinterpret_cast<float4 *>(hi + off + q * 128) = h;
+                    *reinterpret_cast<float4 *>(lo + off + q * 128) = l;
+                }
+                fence_proxy_async();                   // generic-proxy smem writes -> visible to the tensor core
+                mbar_arrive(&full_a[s]);
             }
-            fence_proxy_async();                       // generic-proxy smem writes -> visible to the tensor core
-            mbar_arrive(&full_a[s]);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = nx[q];
-            in = in_nx; rs = rs_nx;
         }
     } else if (warp < 8) {
         // ------------------------------------------------------------------ epilogue (thread = row, own TMEM lane)
