@@ -8,17 +8,19 @@
 //   q       = b0 + 2^8 b1 + 2^16 b2 + 2^24 b3            b0..b2 unsigned bytes, b3 signed (two's complement planes)
 //   G_s[i,j] = sum_{k+l=s} sum_r b_k[r,i] * b_l[r,j]     tcgen05.mma kind::i8, int32 accumulators in TMEM, one
 //                                                        accumulator per power-of-two weight group s = 0..6
-//   sum_r q_i q_j = sum_s 2^(8s) G_s[i,j]                exact; int64 global accumulators, drained every <= 8192 rows
-//   result  = ( sum_r q_i q_j - S_i S_j / n ) / 4^e      S = column sums of q (exact int64), combined in f64
+//   Q[i,j] = sum_r q_i q_j = sum_s 2^(8s) G_s[i,j]       exact; int64 global accumulators, drained every 6144 rows
+//   result  = ( Q - S delta^T - delta S^T + n delta delta^T ) / 4^e     S = exact int64 column sums of q,
+//                                                        delta_j = mean_j 2^e - m_j; combined in f64
 // The only approximation is the input quantisation 2^-e (<= 2^-30 of max|x|, i.e. well below one f32 ulp of a
 // typical element).  Integer accumulation is order-independent, so the result is bit-identical for any slicing,
 // any atomic order and any GPU count.
 //
-// One CTA = a 32-column stripe j of the output for a slice of rows: TMEM holds 2 (M blocks of 128 rows i) x 7
-// (weight groups) accumulators of 128 x 32 int32 = 448 of its 512 columns.  Per 64-row stage the producers
-// (4 warps) quantise all d columns once into four byte planes in the canonical MN-major no-swizzle UMMA layout
-// (8 K-rows x 16 bytes per core matrix); both MMA operands are views of those planes (A: 128 columns of plane k,
-// B: the stripe's 32 columns of plane l).
+// One CTA = a 128 x 64 output tile (row block i, column stripe j) for a slice of rows: TMEM holds the 7 weight-group
+// accumulators of 128 x 64 int32 = 448 of its 512 columns.  Per 32-row stage: 4 loader warps stage the rows (cp.async,
+// 4 stages deep), 8 converter warps quantise all d columns into four byte planes in the canonical MN-major
+// no-swizzle UMMA layout (8 K-rows x 16 bytes per core matrix), one lane issues the 16 tcgen05.mma (both operands are
+// views of the planes: A = the 128 columns of block i in plane k, B = the stripe's 64 columns in plane l), and 4
+// drain warps move the accumulators to int64 global memory every 192 stages.
 #include "device.cuh"
 #include "../../include/cleora_b200.h"
 
@@ -68,14 +70,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
         }
     }
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 // 16-byte LDGSTS (cp.async): measured far faster than UBLKCP (cp.async.bulk) for this access pattern -- the 1-D bulk
 // engine delivered only ~8 B/clk per SM here, which capped the kernel at 4.1 ms regardless of pipeline depth.
 __device__ __forceinline__ void cp_async_cg16(void *dst, const void *src, int src_bytes) {
@@ -86,9 +80,6 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
