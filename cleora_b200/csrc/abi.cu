@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -100,10 +101,16 @@ struct DevBuf {
     ~DevBuf() { free(); }
 };
 
+int64_t env_int64(const char *name, int64_t dflt) {
+    const char *e = getenv(name);
+    return (e && *e) ? atoll(e) : dflt;
+}
+
 void free_device_graph(DeviceGraph *dg) {
     if (!dg) return;
     cudaFree(dg->rowptr); cudaFree(dg->col); cudaFree(dg->left); cudaFree(dg->sym); cudaFree(dg->hash);
-    cudaFree(dg->long_rows); cudaFree(dg->rsum_left); cudaFree(dg->rsum_sym);
+    cudaFree(dg->long_rows); cudaFree(dg->long_chunk_ptr); cudaFree(dg->long_chunk_owner);
+    cudaFree(dg->rsum_left); cudaFree(dg->rsum_sym);
     delete dg;
 }
 
@@ -136,6 +143,32 @@ DeviceGraph &device_graph(Graph &g) {
         if (!g.hash.empty()) {
             CUDA_TRY(cudaMalloc((void **)&dg->hash, g.hash.size() * sizeof(uint64_t)));
             CUDA_TRY(cudaMemcpy(dg->hash, g.hash.data(), g.hash.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        }
+        {   // long-row schedule (degree skew): rows above the threshold are processed chunk-wise by separate warps
+            const int64_t threshold = env_int64("CLEORA_B200_LONG_ROW", 8192), chunk = env_int64("CLEORA_B200_LONG_CHUNK", 2048);
+            std::vector<int64_t> rows, cptr{0};
+            std::vector<int32_t> owner;
+            for (int64_t r = 0; r < g.n_rows; ++r) {
+                const int64_t deg = g.rowptr[(size_t)r + 1] - g.rowptr[(size_t)r];
+                if (deg > threshold) {
+                    const int64_t nc = (deg + chunk - 1) / chunk;
+                    for (int64_t c = 0; c < nc; ++c) owner.push_back((int32_t)rows.size());
+                    rows.push_back(r);
+                    cptr.push_back(cptr.back() + nc);
+                }
+            }
+            dg->long_threshold = threshold;
+            dg->long_chunk_edges = chunk;
+            dg->n_long = (int64_t)rows.size();
+            dg->n_long_chunks = (int64_t)owner.size();
+            if (!rows.empty()) {
+                CUDA_TRY(cudaMalloc((void **)&dg->long_rows, rows.size() * sizeof(int64_t)));
+                CUDA_TRY(cudaMemcpy(dg->long_rows, rows.data(), rows.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMalloc((void **)&dg->long_chunk_ptr, cptr.size() * sizeof(int64_t)));
+                CUDA_TRY(cudaMemcpy(dg->long_chunk_ptr, cptr.data(), cptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMalloc((void **)&dg->long_chunk_owner, owner.size() * sizeof(int32_t)));
+                CUDA_TRY(cudaMemcpy(dg->long_chunk_owner, owner.data(), owner.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            }
         }
     } catch (...) {
         free_device_graph(dg);
@@ -473,6 +506,7 @@ extern "C" int cleora_release_workspace(void) {
         persistent().release();
         Workspace &w = workspace();
         w.colsum_partials.release(); w.gram_partials.release(); w.sqdiff_partials.release(); w.misc.release();
+        w.spmm_partials.release();
     });
 }
 extern "C" int64_t cleora_kernel_launch_count(void) { return g_launches.load(); }

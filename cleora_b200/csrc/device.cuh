@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdint>
+#include <climits>
 #include <string>
 
 namespace cleora {
@@ -17,9 +18,12 @@ struct DeviceGraph {
     uint32_t *col = nullptr;
     float *left = nullptr, *sym = nullptr;
     uint64_t *hash = nullptr;
-    // long-row schedule (rows with more than LONG_ROW_EDGES edges are split across warps)
-    int64_t n_long = 0;
-    int32_t *long_rows = nullptr;
+    // long-row schedule: rows with more than long_threshold edges are split into chunks of long_chunk_edges, one warp
+    // per chunk (kernels.cu); built at upload time
+    int64_t n_long = 0, n_long_chunks = 0, long_threshold = INT64_MAX, long_chunk_edges = 0;
+    int64_t *long_rows = nullptr;          // [n_long] row indices
+    int64_t *long_chunk_ptr = nullptr;     // [n_long + 1] first chunk of each long row
+    int32_t *long_chunk_owner = nullptr;   // [n_long_chunks] index into long_rows
     float *rsum_left = nullptr, *rsum_sym = nullptr;   // A*1 per Markov type, built on first pipelined use
 };
 
@@ -53,8 +57,8 @@ struct Scratch {
     void release();
 };
 struct Workspace {
-    Scratch colsum_partials, gram_partials, sqdiff_partials, misc;
-    size_t bytes() const { return colsum_partials.cap + gram_partials.cap + sqdiff_partials.cap + misc.cap; }
+    Scratch colsum_partials, gram_partials, sqdiff_partials, misc, spmm_partials;
+    size_t bytes() const { return colsum_partials.cap + gram_partials.cap + sqdiff_partials.cap + misc.cap + spmm_partials.cap; }
 };
 Workspace &workspace();
 

@@ -15,6 +15,7 @@
 #include "../../include/cleora_b200.h"
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 #include <string>
 
@@ -58,27 +59,12 @@ __device__ __forceinline__ float norm_scale_factor(float part, int norm) {
 // LPR lanes cooperate on one row (32/LPR rows per warp); each lane owns VEC float4 column groups, so
 // D = 4*LPR*VEC.  Edge (col,val) pairs are fetched LPR at a time with one coalesced load per lane and broadcast
 // by shuffle; X rows are read with 128-bit read-only loads, U rows in flight before the first dependent add.
+// acc += sum over edges [s, e) in stored order (separate multiply and add); all 32 lanes of the warp must call it.
 template <int LPR, int VEC, int U>
-__global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restrict__ rowptr,
-                                                        const uint32_t *__restrict__ col,
-                                                        const float *__restrict__ val, const float *__restrict__ x,
-                                                        float *__restrict__ out, const float *__restrict__ resid,
-                                                        int64_t n_rows, float alpha, float rw, int norm) {
-    constexpr int D4 = LPR * VEC;          // float4 per row
-    constexpr int RPW = 32 / LPR;          // rows per warp
-    const int lane = threadIdx.x & 31;
-    const int gl = lane & (LPR - 1);
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t row = warp * RPW + lane / LPR;
-    const bool valid = row < n_rows;
-    int64_t s = 0, e = 0;
-    if (valid) { s = rowptr[row]; e = rowptr[row + 1]; }
-
-    float4 acc[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 *__restrict__ xv = reinterpret_cast<const float4 *>(x);
-
+__device__ __forceinline__ void accumulate_edges(const uint32_t *__restrict__ col, const float *__restrict__ val,
+                                                 const float4 *__restrict__ xv, int64_t s, int64_t e, int gl,
+                                                 float4 (&acc)[VEC]) {
+    constexpr int D4 = LPR * VEC;
     for (int64_t base = s; __any_sync(FULL, base < e); base += LPR) {
         const int64_t rem = e - base;
         const int cnt = rem > LPR ? LPR : (int)rem;            // <= 0 for groups that are already done
@@ -114,8 +100,14 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restric
             }
         }
     }
+}
 
-    if (resid != nullptr && valid) {                    // dst = alpha*dst + rw*src (embedding.rs:121-129)
+// Epilogue: residual mix (embedding.rs:121-129), row norm, store.  All lanes of the warp must call it.
+template <int LPR, int VEC>
+__device__ __forceinline__ void finish_row(float4 (&acc)[VEC], int64_t row, bool valid, int gl, float *__restrict__ out,
+                                           const float *__restrict__ resid, float alpha, float rw, int norm) {
+    constexpr int D4 = LPR * VEC;
+    if (resid != nullptr && valid) {                    // dst = alpha*dst + rw*src
         const float4 *rp = reinterpret_cast<const float4 *>(resid) + row * D4 + gl;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
@@ -126,7 +118,6 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restric
             acc[v].w = __fadd_rn(__fmul_rn(alpha, acc[v].w), __fmul_rn(rw, r.w));
         }
     }
-
     if (norm != CLEORA_NORM_NONE) {
         float part = 0.f;
         if (norm == CLEORA_NORM_L1_NUMPY) {
@@ -164,6 +155,82 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restric
 #pragma unroll
         for (int v = 0; v < VEC; ++v) op[v * LPR] = acc[v];
     }
+}
+
+// Rows with more than `long_threshold` edges are left to the long-row kernels below (only ever set for LPR == 32).
+template <int LPR, int VEC, int U>
+__global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restrict__ rowptr,
+                                                        const uint32_t *__restrict__ col,
+                                                        const float *__restrict__ val, const float *__restrict__ x,
+                                                        float *__restrict__ out, const float *__restrict__ resid,
+                                                        int64_t n_rows, float alpha, float rw, int norm,
+                                                        int64_t long_threshold) {
+    constexpr int RPW = 32 / LPR;          // rows per warp
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LPR - 1);
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t row = warp * RPW + lane / LPR;
+    bool valid = row < n_rows;
+    int64_t s = 0, e = 0;
+    if (valid) { s = rowptr[row]; e = rowptr[row + 1]; }
+    if (LPR == 32 && e - s > long_threshold) return;            // warp-uniform: one row per warp
+    float4 acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    accumulate_edges<LPR, VEC, U>(col, val, reinterpret_cast<const float4 *>(x), s, e, gl, acc);
+    finish_row<LPR, VEC>(acc, row, valid, gl, out, resid, alpha, rw, norm);
+}
+
+// Long rows (hubs of power-law graphs): one warp per CHUNK of a long row writes a partial sum; one warp per long row
+// then adds the partials in chunk order and runs the usual epilogue.  Deterministic; the summation tree differs from
+// the sequential reference order for these rows only (documented deviation, a few ulp).
+template <int VEC, int U>
+__global__ void __launch_bounds__(256) spmm_long_partial_kernel(const int64_t *__restrict__ rowptr,
+                                                                const uint32_t *__restrict__ col,
+                                                                const float *__restrict__ val,
+                                                                const float *__restrict__ x,
+                                                                const int64_t *__restrict__ long_rows,
+                                                                const int64_t *__restrict__ chunk_ptr,
+                                                                const int32_t *__restrict__ chunk_owner, int64_t n_chunks,
+                                                                int64_t chunk_edges, float *__restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n_chunks) return;
+    const int32_t ri = chunk_owner[c];
+    const int64_t row = long_rows[ri];
+    const int64_t s = rowptr[row] + (c - chunk_ptr[ri]) * chunk_edges;
+    const int64_t e = min(rowptr[row + 1], s + chunk_edges);
+    float4 acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    accumulate_edges<32, VEC, U>(col, val, reinterpret_cast<const float4 *>(x), s, e, lane, acc);
+    float4 *pp = reinterpret_cast<float4 *>(partial) + c * (32 * VEC) + lane;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) pp[v * 32] = acc[v];
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) spmm_long_finish_kernel(const int64_t *__restrict__ long_rows,
+                                                               const int64_t *__restrict__ chunk_ptr, int64_t n_long,
+                                                               const float *__restrict__ partial, float *__restrict__ out,
+                                                               const float *__restrict__ resid, float alpha, float rw,
+                                                               int norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t ri = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ri >= n_long) return;
+    float4 acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t c = chunk_ptr[ri]; c < chunk_ptr[ri + 1]; ++c) {
+        const float4 *pp = reinterpret_cast<const float4 *>(partial) + c * (32 * VEC) + lane;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const float4 p = pp[v * 32];
+            acc[v].x = __fadd_rn(acc[v].x, p.x); acc[v].y = __fadd_rn(acc[v].y, p.y);
+            acc[v].z = __fadd_rn(acc[v].z, p.z); acc[v].w = __fadd_rn(acc[v].w, p.w);
+        }
+    }
+    finish_row<32, VEC>(acc, long_rows[ri], true, lane, out, resid, alpha, rw, norm);
 }
 
 // Any d: one warp per row, lane owns columns lane, lane+32, ... in passes of T*32 columns.  Same accumulation
@@ -226,9 +293,22 @@ static void launch_rows(const DeviceGraph &g, const float *val, const float *x, 
     const int threads = 256;
     const int64_t rows_per_block = (int64_t)(threads / 32) * RPW;
     const int64_t blocks = (g.n_rows + rows_per_block - 1) / rows_per_block;
-    spmm_rows_kernel<LPR, VEC, U><<<(unsigned)blocks, threads, 0, st>>>(g.rowptr, g.col, val, x, out, resid,
-                                                                        g.n_rows, alpha, rw, norm);
+    const bool split = LPR == 32 && g.n_long > 0;
+    spmm_rows_kernel<LPR, VEC, U><<<(unsigned)blocks, threads, 0, st>>>(
+        g.rowptr, g.col, val, x, out, resid, g.n_rows, alpha, rw, norm, split ? g.long_threshold : INT64_MAX);
     LAUNCH_CHECK();
+    if constexpr (LPR == 32) {
+        if (split) {
+            float *partial = (float *)workspace().spmm_partials.get((size_t)g.n_long_chunks * 128 * VEC * sizeof(float));
+            spmm_long_partial_kernel<VEC, U><<<(unsigned)((g.n_long_chunks + 7) / 8), threads, 0, st>>>(
+                g.rowptr, g.col, val, x, g.long_rows, g.long_chunk_ptr, g.long_chunk_owner, g.n_long_chunks,
+                g.long_chunk_edges, partial);
+            LAUNCH_CHECK();
+            spmm_long_finish_kernel<VEC><<<(unsigned)((g.n_long + 7) / 8), threads, 0, st>>>(
+                g.long_rows, g.long_chunk_ptr, g.n_long, partial, out, resid, alpha, rw, norm);
+            LAUNCH_CHECK();
+        }
+    }
 }
 
 void launch_spmm(const DeviceGraph &g, const float *val, const float *x, int64_t d, float *out, const float *resid,

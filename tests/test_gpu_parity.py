@@ -86,6 +86,27 @@ def test_spmm_bit_exact_skewed_rows(skew_pair, d):
     np.testing.assert_array_equal(bits(g.left_markov_propagate(x)), bits(oracle.spmm(o, x, "left")))
 
 
+def test_hub_rows_are_split_deterministically():
+    """Degree skew (SURVEY.md hard part): rows above the long-row threshold (8192 edges) are summed chunk-wise by
+    several warps.  Deterministic, within a few ulp of the sequential order; every other row stays bit-exact."""
+    rs = np.random.default_rng(3)
+    n_leaf = 30000
+    lines = [f"hub {i}" for i in range(n_leaf)] + [f"hub2 {i}" for i in range(0, n_leaf, 3)]
+    lines += [f"{int(a)} {int(b)}" for a, b in rs.integers(0, n_leaf, size=(60000, 2))]
+    g, o = _pair(lines, "complex::reflexive::n")
+    deg = np.diff(o.rowptr)
+    assert deg.max() > 8192 and (deg > 8192).sum() == 2
+    for d in (128, 256):
+        x = rs.standard_normal((o.n, d)).astype(np.float32)
+        got, ref = g.left_markov_propagate(x), oracle.spmm(o, x)
+        short = deg <= 8192
+        np.testing.assert_array_equal(bits(got[short]), bits(ref[short]))
+        np.testing.assert_allclose(got[~short], ref[~short], rtol=2e-5, atol=1e-6 * np.abs(ref).max())
+        np.testing.assert_array_equal(bits(g.left_markov_propagate(x)), bits(got))        # run-to-run identical
+    _assert_1e5(g.embed_fast(128, 40), oracle.embed_fast(o, 128, 40))
+    np.testing.assert_array_equal(bits(g.left_markov_propagate(x[:, :32].copy())), bits(oracle.spmm(o, x[:, :32].copy())))  # d=32: no split
+
+
 def test_spmm_edge_cases():
     # single entity, self loop only; empty graph; d = 0
     g, o = _pair(["a"], "complex::reflexive::n")
