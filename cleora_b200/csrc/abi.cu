@@ -144,8 +144,11 @@ DeviceGraph &device_graph(Graph &g) {
             CUDA_TRY(cudaMalloc((void **)&dg->hash, g.hash.size() * sizeof(uint64_t)));
             CUDA_TRY(cudaMemcpy(dg->hash, g.hash.data(), g.hash.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
         }
-        {   // long-row schedule (degree skew): rows above the threshold are processed chunk-wise by separate warps
-            const int64_t threshold = env_int64("CLEORA_B200_LONG_ROW", 8192), chunk = env_int64("CLEORA_B200_LONG_CHUNK", 2048);
+        {   // long-row schedule (degree skew): rows above the threshold are processed chunk-wise by separate warps.
+            // The default threshold is deliberately high: a chunked f32 sum differs from the reference's sequential
+            // sum by ~sqrt(deg) ulp (measured 1e-5 relative at 30k edges, and that feeds back through 40 iterations on
+            // star-like graphs), so splitting is reserved for hubs whose sequential walk would dominate the launch.
+            const int64_t threshold = env_int64("CLEORA_B200_LONG_ROW", 65536), chunk = env_int64("CLEORA_B200_LONG_CHUNK", 4096);
             std::vector<int64_t> rows, cptr{0};
             std::vector<int32_t> owner;
             for (int64_t r = 0; r < g.n_rows; ++r) {

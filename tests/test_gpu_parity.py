@@ -87,24 +87,37 @@ def test_spmm_bit_exact_skewed_rows(skew_pair, d):
 
 
 def test_hub_rows_are_split_deterministically():
-    """Degree skew (SURVEY.md hard part): rows above the long-row threshold (8192 edges) are summed chunk-wise by
-    several warps.  Deterministic, within a few ulp of the sequential order; every other row stays bit-exact."""
+    """Degree skew (SURVEY.md hard part): rows above the long-row threshold (default 65536 edges; lowered to 8192
+    here) are summed chunk-wise by several warps -- deterministic, every other row still bit-exact.  The chunked f32
+    sum differs from the reference's sequential sum by ~sqrt(deg) ulp on those rows, which is why the default
+    threshold is high: with the default, this graph stays bit-exact and the 40-iteration loop stays within 1e-5."""
     rs = np.random.default_rng(3)
     n_leaf = 30000
     lines = [f"hub {i}" for i in range(n_leaf)] + [f"hub2 {i}" for i in range(0, n_leaf, 3)]
     lines += [f"{int(a)} {int(b)}" for a, b in rs.integers(0, n_leaf, size=(60000, 2))]
-    g, o = _pair(lines, "complex::reflexive::n")
+    o = oracle.build_graph(lines, "complex::reflexive::n")
     deg = np.diff(o.rowptr)
     assert deg.max() > 8192 and (deg > 8192).sum() == 2
-    for d in (128, 256):
-        x = rs.standard_normal((o.n, d)).astype(np.float32)
-        got, ref = g.left_markov_propagate(x), oracle.spmm(o, x)
-        short = deg <= 8192
-        np.testing.assert_array_equal(bits(got[short]), bits(ref[short]))
-        np.testing.assert_allclose(got[~short], ref[~short], rtol=2e-5, atol=1e-6 * np.abs(ref).max())
-        np.testing.assert_array_equal(bits(g.left_markov_propagate(x)), bits(got))        # run-to-run identical
+    x = rs.standard_normal((o.n, 256)).astype(np.float32)
+    ref = oracle.spmm(o, x)
+    g = cb.SparseMatrix.from_iterator(lines, "complex::reflexive::n")                  # default threshold: no split
+    np.testing.assert_array_equal(bits(g.left_markov_propagate(x)), bits(ref))
     _assert_1e5(g.embed_fast(128, 40), oracle.embed_fast(o, 128, 40))
-    np.testing.assert_array_equal(bits(g.left_markov_propagate(x[:, :32].copy())), bits(oracle.spmm(o, x[:, :32].copy())))  # d=32: no split
+    os.environ["CLEORA_B200_LONG_ROW"], os.environ["CLEORA_B200_LONG_CHUNK"] = "8192", "2048"
+    try:
+        gs = cb.SparseMatrix.from_iterator(lines, "complex::reflexive::n")             # schedule is built at upload
+        got = gs.left_markov_propagate(x)
+    finally:
+        del os.environ["CLEORA_B200_LONG_ROW"], os.environ["CLEORA_B200_LONG_CHUNK"]
+    short = deg <= 8192
+    np.testing.assert_array_equal(bits(got[short]), bits(ref[short]))
+    np.testing.assert_allclose(got[~short], ref[~short], rtol=1e-4, atol=1e-6 * np.abs(ref).max())
+    np.testing.assert_array_equal(bits(gs.left_markov_propagate(x)), bits(got))        # run-to-run identical
+    x128 = np.ascontiguousarray(x[:, :128])
+    got128 = gs.left_markov_propagate(x128)
+    np.testing.assert_array_equal(bits(got128[short]), bits(oracle.spmm(o, x128)[short]))
+    x32 = np.ascontiguousarray(x[:, :32])
+    np.testing.assert_array_equal(bits(gs.left_markov_propagate(x32)), bits(oracle.spmm(o, x32)))   # d=32: never split
 
 
 def test_spmm_edge_cases():
