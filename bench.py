@@ -290,10 +290,15 @@ def run_ours(args, w, name):
 
 
 def main():
-    # torchrun exports OMP_NUM_THREADS=1 for every rank; the host-side CSR construction (rank 0 only) and the CPU
-    # baseline are OpenMP code, so give them the cores back (must happen before the libraries initialise OpenMP).
-    if os.environ.get("OMP_NUM_THREADS") == "1" and "WORLD_SIZE" in os.environ:
-        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+    # torchrun exports OMP_NUM_THREADS=1 for every rank.  The host-side CSR construction (rank 0) and the CPU arms are
+    # OpenMP / OpenBLAS code, so give them the cores back -- all of them for the reference arm (only rank 0 works
+    # there), an even share per rank otherwise.  Must happen before the libraries initialise their thread pools.
+    if "WORLD_SIZE" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
+        cores = os.cpu_count() or 1
+        world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+        share = cores if "reference" in sys.argv else max(1, cores // world)
+        os.environ["OMP_NUM_THREADS"] = str(share)
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", str(min(share, 64)))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
