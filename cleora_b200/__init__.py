@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import check, ptr
 from .pycleora import SparseMatrix
 
-__all__ = ["SparseMatrix", "embed", "whiten_embeddings", "embed_using_baseline_cleora", "pinned_empty", "set_option",
+__all__ = ["SparseMatrix", "embed", "whiten_embeddings", "embed_using_baseline_cleora", "pinned_empty", "set_option", "release_workspace",
            "DEFAULT_FEATURE_DIM", "DEFAULT_NUM_ITERATIONS"]
 
 DEFAULT_FEATURE_DIM = 256          # pycleora/__init__.py:12
@@ -29,6 +29,11 @@ def set_option(key: str, value: int) -> None:
     """Library tuning switches (include/cleora_b200.h: cleora_set_option), e.g. ``set_option("pipeline_whiten", 0)``
     keeps the reference's stage order exactly instead of overlapping the eigensolve with the next SpMM."""
     check(_lib.lib().cleora_set_option(key.encode(), int(value)))
+
+
+def release_workspace() -> None:
+    """Free the calling thread's cached device buffers (iterates, whitening scratch, cuSOLVER workspace)."""
+    check(_lib.lib().cleora_release_workspace())
 
 
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
