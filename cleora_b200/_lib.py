@@ -73,6 +73,15 @@ PROTOTYPES = {
     "cleora_dev_init": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "cleora_dev_spmm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,
                                   C.c_float, C.c_int, C.c_void_p]),
+    "cleora_dev_spmm_push": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p), C.c_int,
+                                       C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "cleora_dev_whiten_apply_push": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                               C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cleora_dev_malloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cleora_dev_free": (C.c_int, [C.c_void_p]),
+    "cleora_ipc_get_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "cleora_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "cleora_ipc_close": (C.c_int, [C.c_void_p]),
     "cleora_dev_normalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "cleora_dev_col_sums": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "cleora_dev_centered_gram": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -669,6 +669,53 @@ extern "C" int cleora_dev_spmm(cleora_graph_t *g, int markov, const float *x, in
         launch_spmm(dg, values_of(dg, markov), x, d, out, resid, alpha, rw, normalization, (cudaStream_t)stream);
     });
 }
+static PeerOut make_peers(float *const *extra, int n_extra) {
+    if (n_extra < 0 || n_extra > 7) value_error("at most 7 extra destinations");
+    PeerOut p{};
+    p.n_extra = n_extra;
+    for (int i = 0; i < n_extra; ++i) p.extra[i] = extra[i];
+    return p;
+}
+extern "C" int cleora_dev_spmm_push(cleora_graph_t *g, int markov, const float *x, int64_t d, float *out,
+                                    float *const *extra_outs, int n_extra, const float *resid, float alpha, float rw,
+                                    int normalization, void *stream) {
+    return guarded([&] {
+        check_norm(normalization);
+        DeviceGraph &dg = device_graph(*g);
+        const PeerOut peers = make_peers(extra_outs, n_extra);
+        launch_spmm(dg, values_of(dg, markov), x, d, out, resid, alpha, rw, normalization, (cudaStream_t)stream, &peers);
+    });
+}
+extern "C" int cleora_dev_whiten_apply_push(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
+                                            int64_t dout, float *out, float *const *extra_outs, int n_extra,
+                                            int normalization, const float *rowscale, void *stream) {
+    return guarded([&] {
+        if (!whiten_apply_tc_supported(d, dout)) value_error("fused apply needs d % 32 == 0, dout % 16 == 0, dout <= 256");
+        const PeerOut peers = make_peers(extra_outs, n_extra);
+        launch_whiten_apply_tc(x, n, d, mean_f32, T, dout, out, normalization, rowscale, (cudaStream_t)stream, &peers);
+    });
+}
+// ---- peer memory plumbing (CUDA IPC): buffers that other ranks' kernels write into ------------------------------
+extern "C" int cleora_dev_malloc(size_t nbytes, void **out) {
+    return guarded([&] { require_device(); CUDA_TRY(cudaMalloc(out, nbytes ? nbytes : 1)); });
+}
+extern "C" int cleora_dev_free(void *p) { return guarded([&] { if (p) CUDA_TRY(cudaFree(p)); }); }
+extern "C" int cleora_ipc_get_handle(void *p, unsigned char *handle64) {
+    return guarded([&] {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(cudaIpcGetMemHandle(&h, p));
+        std::memcpy(handle64, &h, 64);
+    });
+}
+extern "C" int cleora_ipc_open(const unsigned char *handle64, void **out) {
+    return guarded([&] {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle64, 64);
+        CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    });
+}
+extern "C" int cleora_ipc_close(void *p) { return guarded([&] { if (p) CUDA_TRY(cudaIpcCloseMemHandle(p)); }); }
 extern "C" int cleora_dev_normalize(const float *x, int64_t n, int64_t d, int normalization, float *out, void *stream) {
     return guarded([&] { check_norm(normalization); launch_normalize(x, n, d, normalization, out, (cudaStream_t)stream); });
 }

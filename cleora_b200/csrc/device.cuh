@@ -27,6 +27,13 @@ struct DeviceGraph {
     float *rsum_left = nullptr, *rsum_sym = nullptr;   // A*1 per Markov type, built on first pipelined use
 };
 
+// Extra destinations of a row-producing kernel: the same rows are also stored at these base pointers (peer GPUs'
+// copies of the gathered matrix, mapped through CUDA IPC) -- the all-gather fused into the producer's epilogue.
+struct PeerOut {
+    float *extra[7];
+    int n_extra;
+};
+
 void set_error(const std::string &msg);
 extern std::atomic<int64_t> g_launches;
 
@@ -65,7 +72,7 @@ Workspace &workspace();
 // ---- launchers (kernels.cu); all enqueue on `st` and throw CudaFail on launch errors -------------------
 void launch_init(const uint64_t *hash, int64_t n, int64_t d, int64_t seed, float *out, cudaStream_t st);
 void launch_spmm(const DeviceGraph &g, const float *val, const float *x, int64_t d, float *out, const float *resid,
-                 float alpha, float rw, int norm, cudaStream_t st);
+                 float alpha, float rw, int norm, cudaStream_t st, const PeerOut *peers = nullptr);
 void launch_normalize(const float *x, int64_t n, int64_t d, int norm, float *out, cudaStream_t st);
 void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool accumulate, cudaStream_t st);
 void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st);
@@ -73,7 +80,7 @@ void launch_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean
                          float *out, cudaStream_t st);
 bool whiten_apply_tc_supported(int64_t d, int64_t dout);
 void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
-                            float *out, int norm, const float *rowscale, cudaStream_t st);
+                            float *out, int norm, const float *rowscale, cudaStream_t st, const PeerOut *peers = nullptr);
 void launch_row_value_sums(const int64_t *rowptr, const float *val, int64_t n, float *out, cudaStream_t st);
 void launch_sq_diff_sum(const float *a, const float *b, int64_t n, bool f64_diff, double *result, cudaStream_t st);
 void launch_build_transform(const double *V, const double *w, int64_t d, int64_t dout, float *T, cudaStream_t st);

@@ -105,7 +105,8 @@ __device__ __forceinline__ void accumulate_edges(const uint32_t *__restrict__ co
 // Epilogue: residual mix (embedding.rs:121-129), row norm, store.  All lanes of the warp must call it.
 template <int LPR, int VEC>
 __device__ __forceinline__ void finish_row(float4 (&acc)[VEC], int64_t row, bool valid, int gl, float *__restrict__ out,
-                                           const float *__restrict__ resid, float alpha, float rw, int norm) {
+                                           const float *__restrict__ resid, float alpha, float rw, int norm,
+                                           const PeerOut &peers) {
     constexpr int D4 = LPR * VEC;
     if (resid != nullptr && valid) {                    // dst = alpha*dst + rw*src
         const float4 *rp = reinterpret_cast<const float4 *>(resid) + row * D4 + gl;
@@ -154,6 +155,14 @@ __device__ __forceinline__ void finish_row(float4 (&acc)[VEC], int64_t row, bool
         float4 *op = reinterpret_cast<float4 *>(out) + row * D4 + gl;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) op[v * LPR] = acc[v];
+#pragma unroll
+        for (int p = 0; p < 7; ++p) {                         // fused all-gather: the same row into the peers' copies
+            if (p < peers.n_extra) {                          // (static indices keep the pointers in the constant bank)
+                float4 *pp = reinterpret_cast<float4 *>(peers.extra[p]) + row * D4 + gl;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) pp[v * LPR] = acc[v];
+            }
+        }
     }
 }
 
@@ -164,7 +173,7 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restric
                                                         const float *__restrict__ val, const float *__restrict__ x,
                                                         float *__restrict__ out, const float *__restrict__ resid,
                                                         int64_t n_rows, float alpha, float rw, int norm,
-                                                        int64_t long_threshold) {
+                                                        int64_t long_threshold, PeerOut peers) {
     constexpr int RPW = 32 / LPR;          // rows per warp
     const int lane = threadIdx.x & 31;
     const int gl = lane & (LPR - 1);
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restric
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     accumulate_edges<LPR, VEC, U>(col, val, reinterpret_cast<const float4 *>(x), s, e, gl, acc);
-    finish_row<LPR, VEC>(acc, row, valid, gl, out, resid, alpha, rw, norm);
+    finish_row<LPR, VEC>(acc, row, valid, gl, out, resid, alpha, rw, norm, peers);
 }
 
 // Long rows (hubs of power-law graphs): one warp per CHUNK of a long row writes a partial sum; one warp per long row
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(256) spmm_long_finish_kernel(const int64_t *__
                                                                const int64_t *__restrict__ chunk_ptr, int64_t n_long,
                                                                const float *__restrict__ partial, float *__restrict__ out,
                                                                const float *__restrict__ resid, float alpha, float rw,
-                                                               int norm) {
+                                                               int norm, PeerOut peers) {
     const int lane = threadIdx.x & 31;
     const int64_t ri = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (ri >= n_long) return;
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(256) spmm_long_finish_kernel(const int64_t *__
             acc[v].z = __fadd_rn(acc[v].z, p.z); acc[v].w = __fadd_rn(acc[v].w, p.w);
         }
     }
-    finish_row<32, VEC>(acc, long_rows[ri], true, lane, out, resid, alpha, rw, norm);
+    finish_row<32, VEC>(acc, long_rows[ri], true, lane, out, resid, alpha, rw, norm, peers);
 }
 
 // Any d: one warp per row, lane owns columns lane, lane+32, ... in passes of T*32 columns.  Same accumulation
@@ -288,14 +297,14 @@ __global__ void __launch_bounds__(256) spmm_generic_kernel(const int64_t *__rest
 
 template <int LPR, int VEC, int U>
 static void launch_rows(const DeviceGraph &g, const float *val, const float *x, float *out, const float *resid,
-                        float alpha, float rw, int norm, cudaStream_t st) {
+                        float alpha, float rw, int norm, cudaStream_t st, const PeerOut &peers) {
     constexpr int RPW = 32 / LPR;
     const int threads = 256;
     const int64_t rows_per_block = (int64_t)(threads / 32) * RPW;
     const int64_t blocks = (g.n_rows + rows_per_block - 1) / rows_per_block;
     const bool split = LPR == 32 && g.n_long > 0;
     spmm_rows_kernel<LPR, VEC, U><<<(unsigned)blocks, threads, 0, st>>>(
-        g.rowptr, g.col, val, x, out, resid, g.n_rows, alpha, rw, norm, split ? g.long_threshold : INT64_MAX);
+        g.rowptr, g.col, val, x, out, resid, g.n_rows, alpha, rw, norm, split ? g.long_threshold : INT64_MAX, peers);
     LAUNCH_CHECK();
     if constexpr (LPR == 32) {
         if (split) {
@@ -305,30 +314,33 @@ static void launch_rows(const DeviceGraph &g, const float *val, const float *x, 
                 g.long_chunk_edges, partial);
             LAUNCH_CHECK();
             spmm_long_finish_kernel<VEC><<<(unsigned)((g.n_long + 7) / 8), threads, 0, st>>>(
-                g.long_rows, g.long_chunk_ptr, g.n_long, partial, out, resid, alpha, rw, norm);
+                g.long_rows, g.long_chunk_ptr, g.n_long, partial, out, resid, alpha, rw, norm, peers);
             LAUNCH_CHECK();
         }
     }
 }
 
 void launch_spmm(const DeviceGraph &g, const float *val, const float *x, int64_t d, float *out, const float *resid,
-                 float alpha, float rw, int norm, cudaStream_t st) {
+                 float alpha, float rw, int norm, cudaStream_t st, const PeerOut *peers_in) {
     if (g.n_rows == 0 || d == 0) return;
+    PeerOut peers{};
+    if (peers_in) peers = *peers_in;
     if (g.n_rows > (int64_t)0x7fffffff * 8) throw CudaFail{"too many rows for one launch"};
     switch (d) {
-        case 8:    launch_rows<2, 1, 2>(g, val, x, out, resid, alpha, rw, norm, st); return;
-        case 16:   launch_rows<4, 1, 4>(g, val, x, out, resid, alpha, rw, norm, st); return;
-        case 32:   launch_rows<8, 1, 8>(g, val, x, out, resid, alpha, rw, norm, st); return;
-        case 64:   launch_rows<16, 1, 8>(g, val, x, out, resid, alpha, rw, norm, st); return;
-        case 96:   launch_rows<8, 3, 4>(g, val, x, out, resid, alpha, rw, norm, st); return;
-        case 128:  launch_rows<32, 1, 8>(g, val, x, out, resid, alpha, rw, norm, st); return;
-        case 192:  launch_rows<16, 3, 4>(g, val, x, out, resid, alpha, rw, norm, st); return;
-        case 256:  launch_rows<32, 2, 4>(g, val, x, out, resid, alpha, rw, norm, st); return;
-        case 384:  launch_rows<32, 3, 4>(g, val, x, out, resid, alpha, rw, norm, st); return;
-        case 512:  launch_rows<32, 4, 4>(g, val, x, out, resid, alpha, rw, norm, st); return;
-        case 1024: launch_rows<32, 8, 2>(g, val, x, out, resid, alpha, rw, norm, st); return;
+        case 8:    launch_rows<2, 1, 2>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
+        case 16:   launch_rows<4, 1, 4>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
+        case 32:   launch_rows<8, 1, 8>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
+        case 64:   launch_rows<16, 1, 8>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
+        case 96:   launch_rows<8, 3, 4>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
+        case 128:  launch_rows<32, 1, 8>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
+        case 192:  launch_rows<16, 3, 4>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
+        case 256:  launch_rows<32, 2, 4>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
+        case 384:  launch_rows<32, 3, 4>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
+        case 512:  launch_rows<32, 4, 4>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
+        case 1024: launch_rows<32, 8, 2>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
         default: break;
     }
+    if (peers.n_extra) throw CudaFail{"peer push needs a vectorised feature dimension (8..1024 as listed)"};
     const int threads = 256;
     const int64_t blocks = (g.n_rows + 7) / 8;
     spmm_generic_kernel<8><<<(unsigned)blocks, threads, 0, st>>>(g.rowptr, g.col, val, x, out, resid, g.n_rows,

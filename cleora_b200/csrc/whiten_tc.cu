@@ -144,7 +144,7 @@ template <int NORM, int SCALED>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const float *__restrict__ mean,
                        const float *__restrict__ rowscale, const float *__restrict__ Bt, int N,
-                       float *__restrict__ out) {
+                       float *__restrict__ out, PeerOut peers) {
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b_bytes = N * BK * 4;                                  // one of hi / lo
@@ -247,6 +247,9 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
                             o.z = __fdiv_rn(o.z, scale); o.w = __fdiv_rn(o.w, scale);
                         }
                         op[j] = o;
+#pragma unroll
+                        for (int p = 0; p < 7; ++p)                 // fused all-gather into the peers' copies
+                            if (p < peers.n_extra) reinterpret_cast<float4 *>(peers.extra[p] + row * (int64_t)N + c0)[j] = o;
                     }
                 }
             }
@@ -319,9 +322,11 @@ bool whiten_apply_tc_supported(int64_t d, int64_t dout) {
 
 // Scratch for the pre-tiled transform lives in the caller's workspace (misc).
 void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
-                            float *out, int norm, const float *rowscale, cudaStream_t st) {
+                            float *out, int norm, const float *rowscale, cudaStream_t st, const PeerOut *peers_in) {
     using namespace tc;
     if (n == 0) return;
+    PeerOut peers{};
+    if (peers_in) peers = *peers_in;
     float *Bt = (float *)workspace().misc.get((size_t)2 * d * dout * sizeof(float));
     const int64_t tot = d * dout;
     prep_transform_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(T, (int)d, (int)dout, Bt);
@@ -332,7 +337,7 @@ void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *m
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
     auto launch = [&](auto kernel) {
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, mean_f32, rowscale, Bt, N, out);
+        kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, mean_f32, rowscale, Bt, N, out, peers);
     };
     const bool l2 = norm == CLEORA_NORM_L2_NUMPY;
     if (norm != CLEORA_NORM_NONE && !l2) throw CudaFail{"tensor-core apply: unsupported fused normalisation"};

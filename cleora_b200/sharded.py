@@ -149,6 +149,25 @@ class CudaBackend:
     def row_scale(self, shard, markov, out):
         check(self.L.cleora_dev_row_scale(shard.graph._handle(), markov, out.data_ptr(), self.stream()))
 
+    # ---- fused all-gather: kernels store their rows into every rank's copy of the gathered matrix (CUDA IPC)
+    def _ptr_array(self, ptrs):
+        arr = (C.c_void_p * max(len(ptrs), 1))(*ptrs)
+        return arr
+
+    def spmm_push(self, shard, markov, x_full, d, out_ptr, extra_ptrs, resid, alpha, rw, norm):
+        check(self.L.cleora_dev_spmm_push(shard.graph._handle(), markov, x_full.data_ptr(), d, out_ptr,
+                                          self._ptr_array(extra_ptrs), len(extra_ptrs),
+                                          None if resid is None else resid.data_ptr(), alpha, rw, norm, self.stream()))
+
+    def apply_push(self, x, n, d, mean32, T, out_ptr, extra_ptrs, norm, rowscale):
+        check(self.L.cleora_dev_whiten_apply_push(x.data_ptr(), n, d, mean32.data_ptr(), T.data_ptr(), d, out_ptr,
+                                                  self._ptr_array(extra_ptrs), len(extra_ptrs), norm,
+                                                  None if rowscale is None else rowscale.data_ptr(), self.stream()))
+
+    def peer_matrix(self, rows, d, dist, group, rank, world):
+        """Two [rows, d] f32 buffers on this GPU whose addresses are mapped into every other rank (ping-pong)."""
+        return PeerMatrix(self, rows, d, dist, group, rank, world)
+
     # streams: eigensolve / gather run beside the main stream in the pipelined loop
     def new_stream(self):
         return self.torch.cuda.Stream(device=self.device)
@@ -163,6 +182,59 @@ class CudaBackend:
         self.torch.cuda.synchronize()
 
 
+class _CudaArray:
+    """__cuda_array_interface__ shim so torch can view library-allocated (IPC-exportable) device memory."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerMatrix:
+    """The gathered iterate in peer-writable memory: buf[b] is this rank's copy b (b = 0, 1), peer[b][p] the address
+    of rank p's copy b as mapped into this process (cudaIpcOpenMemHandle with lazy peer access)."""
+
+    def __init__(self, be, rows, d, dist, group, rank, world):
+        self.be, self.rank, self.world = be, rank, world
+        L = be.L
+        nbytes = max(rows * d * 4, 4)
+        self.ptr, handles = [], []
+        for _ in range(2):
+            p = C.c_void_p()
+            check(L.cleora_dev_malloc(nbytes, C.byref(p)))
+            h = C.create_string_buffer(64)
+            check(L.cleora_ipc_get_handle(p, h))
+            self.ptr.append(p.value)
+            handles.append(h.raw)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, handles, group=group)
+        self.peer, self._opened = [[None] * world for _ in range(2)], []
+        for b in range(2):
+            for p in range(world):
+                if p == rank:
+                    self.peer[b][p] = self.ptr[b]
+                else:
+                    q = C.c_void_p()
+                    check(L.cleora_ipc_open(everyone[p][b], C.byref(q)))
+                    self.peer[b][p] = q.value
+                    self._opened.append(q.value)
+        self.buf = [be.torch.as_tensor(_CudaArray(self.ptr[b], (rows, d)), device=be.device) for b in range(2)]
+
+    def block_ptrs(self, b, block_row0, d):
+        """(own address, [peer addresses]) of the row block starting at block_row0 in copy b."""
+        off = block_row0 * d * 4
+        return self.peer[b][self.rank] + off, [self.peer[b][p] + off for p in range(self.world) if p != self.rank]
+
+    def close(self):
+        L = self.be.L
+        for q in self._opened:
+            L.cleora_ipc_close(q)
+        self._opened = []
+        for p in self.ptr:
+            L.cleora_dev_free(p)
+        self.ptr = []
+
+
 # ------------------------------------------------------------------------------------------------ the loop
 class ShardedEmbedder:
     """Device-resident, row-sharded version of embed() (pycleora/__init__.py:51-127)."""
@@ -174,7 +246,23 @@ class ShardedEmbedder:
         self.shard, self.d, self.group = shard, d, group
         self.be = backend if backend is not None else CudaBackend(torch.cuda.current_device())
         be, s = self.be, shard
-        self.x_full = be.empty((max(s.n_pad, 1), d), torch.float32)      # gathered iterate, padded layout
+        self.pm = None
+        self.cur = 0
+        if (hasattr(be, "peer_matrix") and 1 < s.world <= 8 and s.n_pad > 0 and d in (8, 16, 32, 64, 96, 128, 192, 256, 384, 512, 1024)
+                and os.environ.get("CLEORA_B200_P2P", "1") != "0"):
+            try:
+                self.pm = be.peer_matrix(s.n_pad, d, dist, group, s.rank, s.world)
+            except (RuntimeError, ValueError):
+                self.pm = None
+        ok = torch.tensor([1 if self.pm is not None else 0])
+        if s.world > 1 and hasattr(be, "peer_matrix"):
+            okd = ok.to(be.device)
+            dist.all_reduce(okd, op=dist.ReduceOp.MIN, group=group)          # all ranks or none
+            if int(okd.item()) == 0 and self.pm is not None:
+                self.pm.close()
+                self.pm = None
+        # gathered iterate, padded layout (copy `cur` of the peer-writable pair when the fused gather is available)
+        self.x_full = self.pm.buf[0] if self.pm is not None else be.empty((max(s.n_pad, 1), d), torch.float32)
         self.x_prev = None
         self.y = be.empty((max(s.block, 1), d), torch.float32)           # own block, post SpMM+norm
         self.z = be.empty((max(s.block, 1), d), torch.float32)           # own block, post whitening
@@ -197,6 +285,20 @@ class ShardedEmbedder:
     def _gather(self, block):
         # equal-sized blocks: one NCCL all-gather into the padded matrix
         self.dist.all_gather_into_tensor(self.x_full, block, group=self.group)
+
+    def _push_targets(self):
+        """Addresses of this rank's block in the NEXT copy of the gathered matrix, here and on every peer."""
+        s = self.shard
+        return self.pm.block_ptrs(1 - self.cur, s.rank * s.block, self.d)
+
+    def _flip(self, barrier_group=None):
+        """All ranks have pushed their blocks: make the next copy current (tiny all-reduce = node-wide barrier)."""
+        if not hasattr(self, "_flag"):
+            self._flag = self.be.empty((1,), self.torch.float32)
+            self._flag.zero_()
+        self.dist.all_reduce(self._flag, group=barrier_group if barrier_group is not None else self.group)
+        self.cur = 1 - self.cur
+        self.x_full = self.pm.buf[self.cur]
 
     def run(self, iters: int, markov: int = 0, norm: int = _lib.NORM_L2_NUMPY, seed: int = 0,
             x0: Optional[np.ndarray] = None, residual_weight: float = 0.0, convergence_threshold: float = 0.0,
@@ -223,7 +325,13 @@ class ShardedEmbedder:
             if conv:
                 self.x_prev.copy_(self.x_full)
             t = timers.start("spmm") if timers else None
-            be.spmm(s, markov, self.x_full, d, self.y, self._own(self.x_full) if use_res else None, alpha, rw, norm)
+            pushed = self.pm is not None and not do_whiten
+            if pushed:      # K1 stores its rows straight into every rank's next copy: the all-gather is the epilogue
+                own_ptr, extra = self._push_targets()
+                be.spmm_push(s, markov, self.x_full, d, own_ptr, extra, self._own(self.x_full) if use_res else None,
+                             alpha, rw, norm)
+            else:
+                be.spmm(s, markov, self.x_full, d, self.y, self._own(self.x_full) if use_res else None, alpha, rw, norm)
             if timers:
                 timers.stop(t)
             fresh = self.y
@@ -250,7 +358,10 @@ class ShardedEmbedder:
                     timers.stop(t)
                 fresh = self.z
             t = timers.start("gather") if timers else None
-            self._gather(fresh)
+            if pushed:
+                self._flip()
+            else:
+                self._gather(fresh)
             if timers:
                 timers.stop(t)
             done = it + 1
@@ -311,6 +422,7 @@ class ShardedEmbedder:
         elif s.n_pad:
             be.init(self.hash_pad, s.n_pad, d, seed, self.x_full)
         # iteration 0: Y = rownorm(A X0); gather Y beside the stats
+        push = self.pm is not None and hasattr(be, "apply_push")
         t = timers.start("spmm") if timers else None
         be.spmm(s, markov, self.x_full, d, self.y, None, 1.0, 0.0, _lib.NORM_L2_NUMPY)
         if timers:
@@ -333,21 +445,35 @@ class ShardedEmbedder:
                 timers.stop(t)
             main.wait_stream(side)                                   # T has arrived
             t = timers.start("apply") if timers else None
-            be.apply_ex(w, s.n_local, d, self.mean32, self.T, y2, _lib.NORM_L2_NUMPY, rowscale)
+            if push:
+                # the GEMM's epilogue stores the normalised rows into y2 AND into every peer's next gathered copy;
+                # y2 itself is the own block of this rank's next copy, so the stats below read it in place
+                own_ptr, extra = self._push_targets()
+                y2 = self._own(self.pm.buf[1 - self.cur])
+                be.apply_push(w, s.n_local, d, self.mean32, self.T, own_ptr, extra, _lib.NORM_L2_NUMPY, rowscale)
+            else:
+                be.apply_ex(w, s.n_local, d, self.mean32, self.T, y2, _lib.NORM_L2_NUMPY, rowscale)
             if timers:
                 timers.stop(t)
             comm.wait_stream(main)
             with be.on(comm):
-                dist.all_gather_into_tensor(self.x_full, y2, group=pl["g_gather"])     # next Y, beside the stats
+                if push:
+                    self._flip(pl["g_gather"])                                         # node-wide barrier, beside the stats
+                else:
+                    dist.all_gather_into_tensor(self.x_full, y2, group=pl["g_gather"])  # next Y, beside the stats
             self._stats(y2, timers)
-            y, y2 = y2, y
+            if not push:
+                y, y2 = y2, y
+            else:
+                y = y2
         # final: X_T = (Y - 1 mu^T) T, gathered
         if s.rank == 0:
             be.transform(self.cov, d, self.T)
         dist.broadcast(self.T, src=0, group=self.group)
         main.wait_stream(comm)
-        be.apply(y, s.n_local, d, self.mean32, self.T, y2)
-        self._gather(y2)
+        out_final = self.z if push else y2             # (with the fused gather y aliases the gathered matrix)
+        be.apply(y, s.n_local, d, self.mean32, self.T, out_final)
+        self._gather(out_final)
         return iters
 
     def result(self) -> np.ndarray:

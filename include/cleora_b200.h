@@ -166,6 +166,21 @@ int cleora_dev_init(const uint64_t *hash, int64_t n, int64_t d, int64_t seed, fl
  * The un-normalised product is bit-identical to src/embedding.rs:52-86 (same f32 operation order). */
 int cleora_dev_spmm(cleora_graph_t *g, int markov, const float *x, int64_t d, float *out, const float *resid,
                     float alpha, float rw, int normalization, void *stream);
+/* K1 / K3 with the all-gather fused into the epilogue: every produced row is stored to `out` AND to the same row of
+ * up to 7 `extra_outs` -- the other ranks' copies of the gathered matrix, mapped into this process through CUDA IPC
+ * (peer stores over NVLink).  `out` and each extra pointer address the first row of THIS rank's block. */
+int cleora_dev_spmm_push(cleora_graph_t *g, int markov, const float *x, int64_t d, float *out,
+                         float *const *extra_outs, int n_extra, const float *resid, float alpha, float rw,
+                         int normalization, void *stream);
+int cleora_dev_whiten_apply_push(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
+                                 int64_t dout, float *out, float *const *extra_outs, int n_extra, int normalization,
+                                 const float *rowscale, void *stream);
+/* Device memory that can be exported to the other ranks of the node (cudaMalloc + cudaIpc*); handles are 64 bytes. */
+int cleora_dev_malloc(size_t nbytes, void **out);
+int cleora_dev_free(void *p);
+int cleora_ipc_get_handle(void *p, unsigned char *handle64);
+int cleora_ipc_open(const unsigned char *handle64, void **out);
+int cleora_ipc_close(void *p);
 /* Row normalisation alone (l2_normalize and the postprocess of user-supplied matrices). */
 int cleora_dev_normalize(const float *x, int64_t n, int64_t d, int normalization, float *out, void *stream);
 /* K2a: sums[d] (f64) += column sums of x[n, d]  (deterministic two-stage reduction; `sums` is overwritten
