@@ -422,7 +422,11 @@ class ShardedEmbedder:
         elif s.n_pad:
             be.init(self.hash_pad, s.n_pad, d, seed, self.x_full)
         # iteration 0: Y = rownorm(A X0); gather Y beside the stats
-        push = self.pm is not None and hasattr(be, "apply_push")
+        # Fused gather from the tensor-core GEMM's epilogue exists (apply_push) but is off by default: that epilogue
+        # writes one row per thread (16-byte pieces), which is fine for local HBM and poor over NVLink (measured: 3.5 ms
+        # vs 0.5 ms per GEMM at 2 GPUs), and here the NCCL all-gather is hidden behind the covariance pass anyway.
+        push = (self.pm is not None and hasattr(be, "apply_push")
+                and os.environ.get("CLEORA_B200_P2P_APPLY", "0") == "1")
         t = timers.start("spmm") if timers else None
         be.spmm(s, markov, self.x_full, d, self.y, None, 1.0, 0.0, _lib.NORM_L2_NUMPY)
         if timers:
