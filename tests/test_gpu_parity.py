@@ -120,6 +120,39 @@ def test_hub_rows_are_split_deterministically():
     np.testing.assert_array_equal(bits(gs.left_markov_propagate(x32)), bits(oracle.spmm(o, x32)))   # d=32: never split
 
 
+def test_push_epilogues_replicate_rows(er_pair):
+    """The fused-gather hooks (cleora_dev_spmm_push / cleora_dev_whiten_apply_push) store every produced row into the
+    extra destinations as well -- exercised here with extra buffers on the same GPU (across GPUs the destinations are
+    CUDA-IPC mappings of the peers' buffers: tools/sharded_check.py)."""
+    import ctypes as C
+    import torch
+    g, o = er_pair
+    L = _lib.lib()
+    n, d = o.n, 256
+    x = torch.from_numpy(np.random.default_rng(0).standard_normal((n, d)).astype(np.float32)).cuda()
+    outs = [torch.zeros(n, d, device="cuda") for _ in range(4)]
+    extra = (C.c_void_p * 3)(*[t.data_ptr() for t in outs[1:]])
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.cleora_dev_graph_prepare(g._handle()))
+    _lib.check(L.cleora_dev_spmm_push(g._handle(), 0, x.data_ptr(), d, outs[0].data_ptr(), extra, 3, None, 1.0, 0.0,
+                                      _lib.NORM_L2_RUST, st))
+    torch.cuda.synchronize()
+    ref = oracle.l2_normalize(oracle.spmm(o, x.cpu().numpy()))
+    np.testing.assert_allclose(outs[0].cpu().numpy(), ref, rtol=1e-6, atol=1e-9)
+    for t in outs[1:]:
+        assert torch.equal(t, outs[0])
+    # tensor-core GEMM epilogue
+    mean = torch.zeros(d, device="cuda")
+    T = torch.eye(d, device="cuda").contiguous()
+    zs = [torch.zeros(n, d, device="cuda") for _ in range(3)]
+    extra2 = (C.c_void_p * 2)(*[t.data_ptr() for t in zs[1:]])
+    _lib.check(L.cleora_dev_whiten_apply_push(outs[0].data_ptr(), n, d, mean.data_ptr(), T.data_ptr(), d,
+                                              zs[0].data_ptr(), extra2, 2, _lib.NORM_L2_NUMPY, None, st))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(zs[0].cpu().numpy(), ref, rtol=0, atol=2e-6)      # identity transform, unit rows
+    assert torch.equal(zs[1], zs[0]) and torch.equal(zs[2], zs[0])
+
+
 def test_spmm_edge_cases():
     # single entity, self loop only; empty graph; d = 0
     g, o = _pair(["a"], "complex::reflexive::n")
