@@ -421,7 +421,7 @@ struct SecondStream {
 
 bool pipeline_eligible(int64_t n, int64_t d, int64_t iters, int normalization, int whiten, double residual_weight,
                        double convergence_threshold) {
-    return g_opt_pipeline.load() && g_eigh == nullptr && whiten && n > 1 && iters >= 2 &&
+    return g_opt_pipeline.load() && whiten && n > 1 && iters >= 2 &&
            normalization == CLEORA_NORM_L2_NUMPY && residual_weight == 0.0 && convergence_threshold <= 0.0 &&
            whiten_apply_tc_supported(d, d);
 }
@@ -440,16 +440,30 @@ void embed_pipelined(DeviceGraph &dg, const float *val, int markov, float *cur, 
     ph.begin();
     stats_device(y, n, d, ws, A);
     ph.end(PH_STATS);
+    const bool host_eigh = g_eigh != nullptr;       // e.g. numpy's LAPACK: runs on the CPU while the GPU does the SpMM
     for (int64_t it = 1; it < iters; ++it) {
         CUDA_TRY(cudaEventRecord(B.stats_done, A));
         CUDA_TRY(cudaStreamWaitEvent(B.s, B.stats_done, 0));
-        ph.begin_on(B.s);
-        ws.eig.transform(ws.cov.p, d, d, ws.T.p, B.s);                   // eigensolve || SpMM
-        ph.end_on(PH_EIGH, B.s);
-        CUDA_TRY(cudaEventRecord(B.t_ready, B.s));
-        ph.begin();
-        launch_spmm(dg, val, y, d, w, nullptr, 1.f, 0.f, CLEORA_NORM_NONE, A);      // W = A Y
-        ph.end(PH_SPMM);
+        if (host_eigh) {
+            CUDA_TRY(cudaMemcpyAsync(ws.h_cov.data(), ws.cov.p, sizeof(double) * d * d, cudaMemcpyDeviceToHost, B.s));
+            ph.begin();
+            launch_spmm(dg, val, y, d, w, nullptr, 1.f, 0.f, CLEORA_NORM_NONE, A);  // W = A Y, enqueued before the host blocks
+            ph.end(PH_SPMM);
+            ph.begin_on(B.s);
+            CUDA_TRY(cudaStreamSynchronize(B.s));                                  // covariance on the host
+            transform_from_cov(ws.h_cov.data(), d, d, ws.h_T.data());              // CPU eigensolve || GPU SpMM
+            CUDA_TRY(cudaMemcpyAsync(ws.T.p, ws.h_T.data(), sizeof(float) * d * d, cudaMemcpyHostToDevice, B.s));
+            ph.end_on(PH_EIGH, B.s);
+            CUDA_TRY(cudaEventRecord(B.t_ready, B.s));
+        } else {
+            ph.begin_on(B.s);
+            ws.eig.transform(ws.cov.p, d, d, ws.T.p, B.s);               // eigensolve || SpMM
+            ph.end_on(PH_EIGH, B.s);
+            CUDA_TRY(cudaEventRecord(B.t_ready, B.s));
+            ph.begin();
+            launch_spmm(dg, val, y, d, w, nullptr, 1.f, 0.f, CLEORA_NORM_NONE, A);  // W = A Y
+            ph.end(PH_SPMM);
+        }
         CUDA_TRY(cudaStreamWaitEvent(A, B.t_ready, 0));
         ph.begin();
         launch_whiten_apply_tc(w, n, d, ws.mean32.p, ws.T.p, d, y2, CLEORA_NORM_L2_NUMPY, rowscale, A);
@@ -460,7 +474,14 @@ void embed_pipelined(DeviceGraph &dg, const float *val, int markov, float *cur, 
         std::swap(y, y2);
     }
     ph.begin();
-    ws.eig.transform(ws.cov.p, d, d, ws.T.p, A);
+    if (host_eigh) {
+        CUDA_TRY(cudaMemcpyAsync(ws.h_cov.data(), ws.cov.p, sizeof(double) * d * d, cudaMemcpyDeviceToHost, A));
+        CUDA_TRY(cudaStreamSynchronize(A));
+        transform_from_cov(ws.h_cov.data(), d, d, ws.h_T.data());
+        CUDA_TRY(cudaMemcpyAsync(ws.T.p, ws.h_T.data(), sizeof(float) * d * d, cudaMemcpyHostToDevice, A));
+    } else {
+        ws.eig.transform(ws.cov.p, d, d, ws.T.p, A);
+    }
     ph.end(PH_EIGH);
     ph.begin();
     launch_whiten_apply(y, n, d, ws.mean32.p, ws.T.p, d, cur, A);          // X_T = (Y - 1 mu^T) T
