@@ -202,6 +202,9 @@ def run_ours(args, w, name):
                                       None if t is None else t.ctypes.data_as(_lib.c_f64p)))
 
     _lib.check(L.cleora_dev_graph_prepare(g._handle()))                 # CSR resident before the timed region
+    host_eigh = _lib.auto_host_eigh(n, d, iters, norm, bool(args.whiten), 0.0, 0.0)   # what cleora_b200.embed() would pick
+    eigh_ctx = _lib.host_eigh(host_eigh)
+    eigh_ctx.__enter__()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     torch.cuda.synchronize()
@@ -221,6 +224,7 @@ def run_ours(args, w, name):
     t_wall = time.perf_counter() - t_wall
     launches = L.cleora_kernel_launch_count() - launches0
     clk = clocks.stop()
+    eigh_ctx.__exit__(None, None, None)
     ms_step = ev0.elapsed_time(ev1) / args.steps
     value = E * iters / (ms_step * 1e-3)
 
@@ -270,7 +274,7 @@ def run_ours(args, w, name):
         "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "nodes": n, "edges": E, "nnz": nnz, "d": d, "iters": iters,
-                   "whiten": bool(args.whiten), "eigh": os.environ.get("CLEORA_B200_EIGH", "cusolver"),
+                   "whiten": bool(args.whiten), "eigh": _lib.eigh_mode() + (" -> numpy LAPACK on the host, overlapped with the SpMM" if host_eigh else " -> cuSOLVER"),
                    "pipeline_whiten": os.environ.get("CLEORA_B200_PIPELINE", "1") != "0",
                    "l2_flush": "inputs (X 1.0 GB + CSR 0.33 GB per iteration) exceed the 126 MB L2"},
         "nnz_per_s": nnz * iters / (ms_step * 1e-3),

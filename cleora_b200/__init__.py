@@ -123,14 +123,13 @@ def embed(
     else:
         x0 = None
 
-    # The rmse early stop on the whitened path compares successive iterates element-wise, so it depends on the
-    # eigensolver's sign/ordering conventions; to stop at the reference's iteration the reference's own LAPACK eigh
-    # is used for such calls (otherwise: cuSOLVER on the device, no host round trip).
+    # Eigensolver choice (see _lib.eigh_mode): the rmse early stop on the whitened path compares successive iterates
+    # element-wise, so it depends on the eigensolver's sign conventions -- such calls use the reference's own LAPACK
+    # eigh; the pipelined default loop also uses it (on the host, hidden behind the SpMM); otherwise cuSOLVER.
     lapack = whiten and convergence_threshold > 0
     if callback is None:
-        with _lib.host_eigh(lapack):
-            out, _ = graph.embed_device(feature_dim, num_iterations, propagation, _DEVICE_NORMS[normalization], seed,
-                                        x0, residual_weight, convergence_threshold, whiten)
+        out, _ = graph.embed_device(feature_dim, num_iterations, propagation, _DEVICE_NORMS[normalization], seed,
+                                    x0, residual_weight, convergence_threshold, whiten)
         return out
 
     # per-iteration path: one device-resident iteration at a time so the callback sees every iterate

@@ -148,7 +148,7 @@ def lib():
         fn.restype = res
         fn.argtypes = args
     _eigh_keepalive = EIGH_FN(_numpy_eigh)
-    if os.environ.get("CLEORA_B200_EIGH", "cusolver") == "numpy":
+    if eigh_mode() == "numpy":
         L.cleora_set_eigh(_eigh_keepalive, None)
     if os.environ.get("CLEORA_B200_PIPELINE", "1") == "0":
         L.cleora_set_option(b"pipeline_whiten", 0)
@@ -156,11 +156,32 @@ def lib():
     return L
 
 
+def eigh_mode() -> str:
+    """CLEORA_B200_EIGH: "auto" (default), "numpy" (always the reference's LAPACK call, on the host) or "cusolver"
+    (always cuSOLVER Dsyevd on the device).  auto = LAPACK on the host where the loop can hide it behind the SpMM
+    (single-GPU pipelined loop: measured 400 vs 444 ms per C2 step) or where the reference's sign convention matters
+    (rmse early stop on whitened iterates); cuSOLVER everywhere else (multi-GPU ranks, standalone whitening)."""
+    m = os.environ.get("CLEORA_B200_EIGH", "auto")
+    return m if m in ("auto", "numpy", "cusolver") else "auto"
+
+
+def auto_host_eigh(n: int, d: int, iters: int, norm: int, whiten: bool, residual_weight: float,
+                   convergence_threshold: float) -> bool:
+    """Would the default single-GPU loop run pipelined (abi.cu: pipeline_eligible) or need LAPACK's conventions?"""
+    if not whiten or eigh_mode() == "cusolver":
+        return False
+    if convergence_threshold > 0:
+        return True
+    return (eigh_mode() == "auto" and n > 1 and iters >= 2 and norm == NORM_L2_NUMPY and residual_weight == 0
+            and os.environ.get("CLEORA_B200_PIPELINE", "1") != "0"
+            and bool(lib().cleora_whiten_apply_fusable(d, d)))
+
+
 class host_eigh:
     """Context manager: route the whitening eigensolve through numpy's LAPACK (the reference's call) while active."""
 
     def __init__(self, enable: bool = True):
-        self.enable = enable and os.environ.get("CLEORA_B200_EIGH", "cusolver") != "numpy"
+        self.enable = enable and eigh_mode() != "numpy"
 
     def __enter__(self):
         if self.enable:

@@ -115,7 +115,6 @@ class SparseMatrix:
         col = np.ascontiguousarray(col, np.uint32)
         val_left = np.ascontiguousarray(val_left, np.float32)
         n_rows = rowptr.shape[0] - 1
-        opt = lambda a, dt, ct: (None if a is None else ptr(np.ascontiguousarray(a, dt), ct))  # noqa: E731
         keep = [np.ascontiguousarray(a, dt) if a is not None else None
                 for a, dt in ((val_sym, np.float32), (row_sum, np.float32), (entity_hash, np.uint64))]
         h = C.c_void_p()
@@ -125,7 +124,6 @@ class SparseMatrix:
             None if keep[1] is None else ptr(keep[1], _lib.c_f32p),
             None if keep[2] is None else ptr(keep[2], _lib.c_u64p),
             n_rows, n_rows if n_cols is None else int(n_cols), int(row_offset), C.byref(h)))
-        del opt
         return SparseMatrix._adopt(h)
 
     # ------------------------------------------------------------------------------------------ introspection
@@ -302,11 +300,14 @@ class SparseMatrix:
         if out is None:
             out = np.empty((self.num_entities, d), np.float32)
         done = C.c_int64(0)
-        check(_lib.lib().cleora_embed(self._handle(), None if x0 is None else ptr(x0, _lib.c_f32p), d,
-                                      int(num_iterations), m, int(seed), float(residual_weight),
-                                      float(convergence_threshold), int(normalization), 1 if whiten else 0,
-                                      ptr(out, _lib.c_f32p), C.byref(done),
-                                      None if timings is None else ptr(timings, _lib.c_f64p)))
+        host = _lib.auto_host_eigh(self.num_entities, d, int(num_iterations), int(normalization), bool(whiten),
+                                   float(residual_weight), float(convergence_threshold))
+        with _lib.host_eigh(host):
+            check(_lib.lib().cleora_embed(self._handle(), None if x0 is None else ptr(x0, _lib.c_f32p), d,
+                                          int(num_iterations), m, int(seed), float(residual_weight),
+                                          float(convergence_threshold), int(normalization), 1 if whiten else 0,
+                                          ptr(out, _lib.c_f32p), C.byref(done),
+                                          None if timings is None else ptr(timings, _lib.c_f64p)))
         return out, int(done.value)
 
     # ------------------------------------------------------------------------------------------ pickle (bincode 1.3.3)
