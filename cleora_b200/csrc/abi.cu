@@ -122,6 +122,15 @@ DeviceGraph &device_graph(Graph &g) {
     CUDA_TRY(cudaGetDevice(&dev));
     if (g.dev && g.dev->device != dev) { free_device_graph(g.dev); g.dev = nullptr; }
     if (g.dev) return *g.dev;
+    if (!g.host_pinned && env_int64("CLEORA_B200_PIN_CSR", 1) != 0 && g.nnz() >= (1 << 20)) {
+        // page-lock the host CSR once: uploads then run at PCIe speed instead of through the pageable staging path
+        auto pin = [](const void *p, size_t bytes) { if (bytes) { if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) cudaGetLastError(); } };
+        pin(g.rowptr.data(), g.rowptr.size() * sizeof(int64_t));
+        pin(g.col.data(), g.col.size() * sizeof(uint32_t));
+        pin(g.left.data(), g.left.size() * sizeof(float));
+        pin(g.sym.data(), g.sym.size() * sizeof(float));
+        g.host_pinned = true;
+    }
     auto *dg = new DeviceGraph();
     dg->device = dev;
     dg->n_rows = g.n_rows; dg->n_cols = g.n_cols; dg->nnz = g.nnz(); dg->row_offset = g.row_offset;
@@ -592,6 +601,11 @@ extern "C" int cleora_graph_from_csr(const int64_t *rowptr, const uint32_t *col,
 extern "C" void cleora_graph_destroy(cleora_graph_t *g) {
     if (!g) return;
     free_device_graph(g->dev);
+    if (g->host_pinned) {
+        for (const void *p : {(const void *)g->rowptr.data(), (const void *)g->col.data(), (const void *)g->left.data(),
+                              (const void *)g->sym.data()})
+            if (p && cudaHostUnregister(const_cast<void *>(p)) != cudaSuccess) cudaGetLastError();
+    }
     delete static_cast<Graph *>(g);
 }
 extern "C" int cleora_graph_release_device(cleora_graph_t *g) {

@@ -37,6 +37,7 @@ struct Graph {
     std::vector<std::string> ids;         // n_rows (may be empty for adopted CSR)
     std::unordered_map<std::string, int64_t> id_index;   // built lazily by find()
     DeviceGraph *dev = nullptr;           // lazily uploaded copy, owned
+    bool host_pinned = false;             // CSR arrays page-locked (cudaHostRegister) for fast (re-)uploads
     int64_t nnz() const { return (int64_t)col.size(); }
 };
 
