@@ -16,8 +16,9 @@ from . import _lib
 from ._lib import check, ptr
 from .pycleora import SparseMatrix
 
-__all__ = ["SparseMatrix", "embed", "whiten_embeddings", "embed_using_baseline_cleora", "pinned_empty", "set_option", "release_workspace",
-           "DEFAULT_FEATURE_DIM", "DEFAULT_NUM_ITERATIONS"]
+__all__ = ["SparseMatrix", "embed", "whiten_embeddings", "embed_using_baseline_cleora", "embed_multiscale",
+           "embed_with_node_features", "embed_inductive", "update_graph", "pinned_empty", "set_option",
+           "release_workspace", "DEFAULT_FEATURE_DIM", "DEFAULT_NUM_ITERATIONS"]
 
 DEFAULT_FEATURE_DIM = 256          # pycleora/__init__.py:12
 DEFAULT_NUM_ITERATIONS = 40        # pycleora/__init__.py:13
@@ -145,3 +146,6 @@ def embed(
             if float(np.sqrt(np.mean(diff * diff))) < convergence_threshold:   # _compute_rmse, :974-976
                 break
     return embeddings
+
+
+from .callers import embed_inductive, embed_multiscale, embed_with_node_features, update_graph  # noqa: E402

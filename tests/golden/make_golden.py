@@ -237,6 +237,30 @@ def make_reference_runs():
         np.savez_compressed(os.path.join(HERE, f"embed_{name}.npz"), **save)
         print(f"embed_{name}.npz written: out {out.shape}")
 
+    # callers that share the loop: multiscale taps, node-feature start, inductive warm start
+    g = SM.from_iterator(iter(karate["edges"]), karate["columns"])
+    ids = g.entity_ids
+    rs = np.random.default_rng(21)
+    feats = {eid: rs.standard_normal(8).astype(np.float32) for eid in ids[::3]}
+    feats["not-in-graph"] = np.zeros(8, np.float32)
+    old_lines, new_lines = list(karate["edges"][:60]), list(karate["edges"][60:]) + ["34 35", "35 1"]
+    g_old = SM.from_iterator(iter(old_lines), karate["columns"])
+    trained = ref.embed(g_old, feature_dim=8, num_iterations=4)
+    np.random.seed(1234)
+    drawn = np.random.randn(36, 8)
+    np.random.seed(1234)
+    g_new, ind = ref.embed_inductive(g_old, trained, old_lines, new_lines, karate["columns"], num_iterations=3)
+    np.savez_compressed(
+        os.path.join(HERE, "callers.npz"), lines=np.array(karate["edges"]), columns=np.array(karate["columns"]),
+        multiscale_w=ref.embed_multiscale(g, feature_dim=8, scales=[4, 2, 5]),
+        multiscale_now=ref.embed_multiscale(g, feature_dim=16, scales=[3, 9], whiten=False, propagation="symmetric"),
+        feat_ids=np.array(list(feats.keys())), feat_vals=np.stack(list(feats.values())),
+        node_features=ref.embed_with_node_features(g, feats, num_iterations=4, feature_weight=0.3),
+        old_lines=np.array(old_lines), new_lines=np.array(new_lines), trained=trained,
+        inductive_ids=np.array(g_new.entity_ids), inductive=ind, inductive_seed=np.int64(1234),
+        inductive_draw_shape=np.array(drawn.shape))
+    print("callers.npz written")
+
     # stage-wise whitening fixture: reference whiten_embeddings + _normalize on a fixed random matrix
     rs = np.random.default_rng(5)
     x = rs.standard_normal((3000, 48)).astype(np.float32) * np.linspace(0.5, 3.0, 48, dtype=np.float32) + 0.3
