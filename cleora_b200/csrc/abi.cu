@@ -340,9 +340,10 @@ void whiten_device(const float *Y, int64_t n, int64_t d, int64_t dout, float *Z,
                    Phase &ph) {
     ws.ensure(d, dout);
     ph.begin();
-    launch_col_sums(Y, n, d, ws.sums.p, false, st);
+    AbsmaxPartials mx;
+    launch_col_sums(Y, n, d, ws.sums.p, false, st, &mx);
     launch_scale_f64(ws.sums.p, d, 1.0 / (double)n, st);                 // mean (f64)
-    launch_centered_gram(Y, n, d, ws.sums.p, ws.cov.p, st);
+    launch_centered_gram(Y, n, d, ws.sums.p, ws.cov.p, st, &mx);
     launch_scale_f64(ws.cov.p, d * d, 1.0 / (double)(n - 1), st);        // cov *= 1/(n-1)
     launch_f64_to_f32(ws.sums.p, ws.mean32.p, d, st);                    // mean.astype(float32)
     ph.end(PH_STATS);
@@ -387,9 +388,10 @@ std::atomic<int> g_opt_pipeline{1};
 
 // mean / covariance of Y (device) into ws.sums (mean, f64), ws.mean32, ws.cov (scaled by 1/(n-1))
 void stats_device(const float *Y, int64_t n, int64_t d, WhitenState &ws, cudaStream_t st) {
-    launch_col_sums(Y, n, d, ws.sums.p, false, st);
+    AbsmaxPartials mx;                                   // max|Y| rides on the column-sum pass
+    launch_col_sums(Y, n, d, ws.sums.p, false, st, &mx);
     launch_scale_f64(ws.sums.p, d, 1.0 / (double)n, st);
-    launch_centered_gram(Y, n, d, ws.sums.p, ws.cov.p, st);
+    launch_centered_gram(Y, n, d, ws.sums.p, ws.cov.p, st, &mx);
     launch_scale_f64(ws.cov.p, d * d, 1.0 / (double)(n - 1), st);
     launch_f64_to_f32(ws.sums.p, ws.mean32.p, d, st);
 }
@@ -539,7 +541,7 @@ extern "C" int cleora_release_workspace(void) {
         persistent().release();
         Workspace &w = workspace();
         w.colsum_partials.release(); w.gram_partials.release(); w.sqdiff_partials.release(); w.misc.release();
-        w.spmm_partials.release();
+        w.spmm_partials.release(); w.absmax_partials.release();
     });
 }
 extern "C" int64_t cleora_kernel_launch_count(void) { return g_launches.load(); }

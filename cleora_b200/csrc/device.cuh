@@ -64,8 +64,10 @@ struct Scratch {
     void release();
 };
 struct Workspace {
-    Scratch colsum_partials, gram_partials, sqdiff_partials, misc, spmm_partials;
-    size_t bytes() const { return colsum_partials.cap + gram_partials.cap + sqdiff_partials.cap + misc.cap + spmm_partials.cap; }
+    Scratch colsum_partials, gram_partials, sqdiff_partials, misc, spmm_partials, absmax_partials;
+    size_t bytes() const {
+        return colsum_partials.cap + gram_partials.cap + sqdiff_partials.cap + misc.cap + spmm_partials.cap + absmax_partials.cap;
+    }
 };
 Workspace &workspace();
 
@@ -74,8 +76,16 @@ void launch_init(const uint64_t *hash, int64_t n, int64_t d, int64_t seed, float
 void launch_spmm(const DeviceGraph &g, const float *val, const float *x, int64_t d, float *out, const float *resid,
                  float alpha, float rw, int norm, cudaStream_t st, const PeerOut *peers = nullptr);
 void launch_normalize(const float *x, int64_t n, int64_t d, int norm, float *out, cudaStream_t st);
-void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool accumulate, cudaStream_t st);
-void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st);
+// Per-block maxima of |x| (device), a by-product of the column-sum pass that the integer Gram kernel needs for its
+// fixed-point scale; count == 0 means "not produced" (the Gram launcher then makes its own pass).
+struct AbsmaxPartials {
+    const float *p = nullptr;
+    int count = 0;
+};
+void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool accumulate, cudaStream_t st,
+                     AbsmaxPartials *absmax = nullptr);
+void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st,
+                          const AbsmaxPartials *absmax = nullptr);
 void launch_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
                          float *out, cudaStream_t st);
 bool whiten_apply_tc_supported(int64_t d, int64_t dout);

@@ -193,9 +193,16 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_mb = d / 128;
-    const int mb = blockIdx.x % n_mb;                                 // output row block i (128 columns of x)
-    const int js = blockIdx.x / n_mb;                                 // output column stripe j (64 columns of x)
+    // Tile (mb, js) = output row block i (128 columns of x) x output column stripe j (64 columns of x).  The Gram
+    // matrix is symmetric group by group (the (k,l) sum is), so only stripes at or right of the diagonal block are
+    // computed; the combine kernel mirrors the rest.  Tiles are numbered row block by row block.
+    const int n_mb = d / 128, n_js = d / STRIPE;
+    int mb = 0, js = 0;
+    for (int t = blockIdx.x; mb < n_mb; ++mb) {
+        const int first = mb * (128 / STRIPE), cnt = n_js - first;
+        if (t < cnt) { js = first + t; break; }
+        t -= cnt;
+    }
     const bool owns_colsum = blockIdx.x == 0;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice, r1 = min(n, r0 + rows_per_slice);
     const int n_stages = (int)((r1 - r0 + ROWS - 1) / ROWS);
@@ -396,8 +403,10 @@ __global__ void gram_i8_combine_kernel(const long long *__restrict__ G, const lo
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)d * d) return;
     const int i = (int)(idx / d), j = (int)(idx - (int64_t)i * d);
+    // tiles left of the diagonal block were not computed: G_s[i][j] = G_s[j][i]
+    const int64_t src = (j / 128 < i / 128) ? (int64_t)j * d + i : idx;
     double acc = 0.0;
-    for (int s = 0; s < g8::GROUPS; ++s) acc += ldexp((double)G[(int64_t)s * d * d + idx], 8 * s);   // small to large
+    for (int s = 0; s < g8::GROUPS; ++s) acc += ldexp((double)G[(int64_t)s * d * d + src], 8 * s);   // small to large
     const double di = ldexp(mean[i], qp->e) - (double)m_int[i], dj = ldexp(mean[j], qp->e) - (double)m_int[j];
     acc += -(double)colsum[i] * dj - di * (double)colsum[j] + (double)n * di * dj;
     cov[idx] = ldexp(acc, -2 * qp->e);
@@ -405,27 +414,34 @@ __global__ void gram_i8_combine_kernel(const long long *__restrict__ G, const lo
 
 bool gram_i8_supported(int64_t n, int64_t d) { return (d == 128 || d == 256) && n >= 4096; }
 
-void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st) {
+void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st,
+                             const AbsmaxPartials *known_absmax) {
     using namespace g8;
     // scratch: absmax partials | QuantParams | m_int[d] | colsum[d] | G[7][d][d]
-    const int nb = 148 * 4;
+    int nb = 148 * 4;
     const size_t off_qp = 1024 * sizeof(float);
     const size_t off_m = off_qp + sizeof(QuantParams);
     const size_t off_cs = off_m + sizeof(int32_t) * 512;
     const size_t off_G = off_cs + sizeof(long long) * 512;
     const size_t total = off_G + sizeof(long long) * GROUPS * d * d;
     unsigned char *ws = (unsigned char *)workspace().gram_partials.get(total);
-    float *absmax = (float *)ws;
+    const float *absmax = (const float *)ws;
     QuantParams *qp = (QuantParams *)(ws + off_qp);
     int32_t *m_int = (int32_t *)(ws + off_m);
     long long *colsum = (long long *)(ws + off_cs);
     long long *G = (long long *)(ws + off_G);
     CUDA_TRY(cudaMemsetAsync(ws + off_cs, 0, total - off_cs, st));
-    absmax_stage1<<<nb, 256, 0, st>>>(x, n * d, absmax);
-    LAUNCH_CHECK();
+    if (known_absmax && known_absmax->count > 0) {                   // the column-sum pass over the same matrix made them
+        absmax = known_absmax->p;
+        nb = known_absmax->count;
+    } else {
+        absmax_stage1<<<nb, 256, 0, st>>>(x, n * d, (float *)ws);
+        LAUNCH_CHECK();
+    }
     quant_params_kernel<<<1, 256, 0, st>>>(absmax, nb, mean, (int)d, qp, m_int);
     LAUNCH_CHECK();
-    const int stripes = (int)(d / STRIPE) * (int)(d / 128);          // tiles: (128-row block i) x (64-column stripe j)
+    int stripes = 0;                                                  // tiles: (128-row block i) x (64-column stripe j >= block i)
+    for (int mb = 0; mb < (int)(d / 128); ++mb) stripes += (int)(d / STRIPE) - mb * (128 / STRIPE);
     int64_t slices = std::max<int64_t>(1, std::min<int64_t>(148 / stripes, (n + 4 * ROWS - 1) / (4 * ROWS)));   // one wave
     const int64_t rows_per_slice = ((n + slices - 1) / slices + ROWS - 1) / ROWS * ROWS;
     slices = (n + rows_per_slice - 1) / rows_per_slice;

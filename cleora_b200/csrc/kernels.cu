@@ -379,24 +379,41 @@ void launch_normalize(const float *x, int64_t n, int64_t d, int norm, float *out
 // Stage 1: every warp of the grid walks rows warp, warp+W, ... and keeps f64 partial sums of its columns
 // (lane owns columns lane, lane+32, ...).  Stage 2: one thread per column adds the W partials in warp order.
 // Deterministic for a fixed launch shape.
+// `absmax` (nullable, one float per block): max |x| over the elements this block read -- free here, and it saves the
+// integer Gram kernel a pass of its own.
 template <int T>
 __global__ void __launch_bounds__(256) col_sums_stage1(const float *__restrict__ x, int64_t n, int d, int c0,
-                                                       double *__restrict__ partial) {
+                                                       double *__restrict__ partial, float *__restrict__ absmax) {
     const int lane = threadIdx.x & 31;
     const int64_t W = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     double acc[T];
+    float mx = 0.f;
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
     for (int64_t r = w; r < n; r += W) {
         const float *xr = x + r * d + c0 + lane;
 #pragma unroll
         for (int t = 0; t < T; ++t)
-            if (c0 + t * 32 + lane < d) acc[t] += (double)__ldg(xr + t * 32);
+            if (c0 + t * 32 + lane < d) {
+                const float v = __ldg(xr + t * 32);
+                acc[t] += (double)v;
+                mx = fmaxf(mx, fabsf(v));
+            }
     }
 #pragma unroll
     for (int t = 0; t < T; ++t)
         if (c0 + t * 32 + lane < d) partial[w * d + c0 + t * 32 + lane] = acc[t];
+    if (absmax != nullptr) {                                   // uniform branch; all 8 warps reach the barrier
+        __shared__ float sh_mx[8];
+        for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        if (lane == 0) sh_mx[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int q = 1; q < 8; ++q) mx = fmaxf(mx, sh_mx[q]);
+            absmax[blockIdx.x] = mx;
+        }
+    }
 }
 
 // blockDim = (32 columns, 8 parts): thread (c, p) adds the partials w = p, p+8, ... of its column (coalesced over c),
@@ -419,15 +436,23 @@ __global__ void __launch_bounds__(256) col_sums_stage2(const double *__restrict_
     }
 }
 
-void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool accumulate, cudaStream_t st) {
+void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool accumulate, cudaStream_t st,
+                     AbsmaxPartials *absmax) {
+    if (absmax) *absmax = AbsmaxPartials{};
     if (d == 0) return;
     const int threads = 256;
     int64_t blocks = std::min<int64_t>((n + 7) / 8, 148 * 4);
     if (blocks < 1) blocks = 1;
     const int64_t W = blocks * (threads / 32);
     double *partial = (double *)workspace().colsum_partials.get(size_t(W) * size_t(d) * sizeof(double));
+    float *mx = nullptr;
+    if (absmax && d <= 8 * 32 && n > 0) {                      // one column pass covers the whole matrix
+        mx = (float *)workspace().absmax_partials.get(size_t(blocks) * sizeof(float));
+        absmax->p = mx;
+        absmax->count = (int)blocks;
+    }
     for (int c0 = 0; c0 < (int)d; c0 += 8 * 32) {
-        col_sums_stage1<8><<<(unsigned)blocks, threads, 0, st>>>(x, n, (int)d, c0, partial);
+        col_sums_stage1<8><<<(unsigned)blocks, threads, 0, st>>>(x, n, (int)d, c0, partial, mx);
         LAUNCH_CHECK();
     }
     col_sums_stage2<<<(unsigned)((d + 31) / 32), dim3(32, 8), 0, st>>>(partial, W, (int)d, sums, accumulate ? 1 : 0);
@@ -679,14 +704,16 @@ __global__ void gram_reduce_kernel(const double *__restrict__ partial, int slice
 }
 
 bool gram_i8_supported(int64_t n, int64_t d);
-void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st);
+void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st,
+                             const AbsmaxPartials *absmax);
 
-void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st) {
+void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st,
+                          const AbsmaxPartials *absmax) {
     if (d == 0) return;
     {   // exact-integer tcgen05 path for the large, common shapes; CLEORA_B200_GRAM=v3|v2 forces the FP64 DMMA kernels
         static const bool allow_i8 = [] { const char *e = getenv("CLEORA_B200_GRAM"); return !e || std::string(e) == "i8"; }();
         if (allow_i8 && gram_i8_supported(n, d) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-            launch_centered_gram_i8(x, n, d, mean, cov, st);
+            launch_centered_gram_i8(x, n, d, mean, cov, st, absmax);
             return;
         }
     }
