@@ -109,8 +109,9 @@ _blas_ctl = None
 def _numpy_eigh(a_ptr, w_ptr, d, _user):
     """numpy.linalg.eigh behind the C callback -- the very call the reference makes
     (pycleora/__init__.py:145), so eigenvector signs/order follow the same LAPACK.  The d x d problem is far too
-    small for a 100+-thread BLAS pool (measured 55 ms at d=256 on a 128-thread host vs ~5 ms with 4 threads), so
-    the call runs under a thread limit (CLEORA_B200_EIGH_THREADS, default 4)."""
+    small for a 100+-thread BLAS pool (measured at d=256 on the 128-thread GPU host: 17-55 ms unrestricted, 5.1 ms
+    with 4 threads, 4.6 ms with 1; profiles/r1h_eigh_probe.txt), so the call runs under a thread limit
+    (CLEORA_B200_EIGH_THREADS, default 1)."""
     global _blas_ctl
     try:
         a = np.ctypeslib.as_array(a_ptr, shape=(d, d))
@@ -122,7 +123,7 @@ def _numpy_eigh(a_ptr, w_ptr, d, _user):
             except Exception:  # noqa: BLE001
                 _blas_ctl = False
         if _blas_ctl:
-            with _blas_ctl.limit(limits=int(os.environ.get("CLEORA_B200_EIGH_THREADS", "4")), user_api="blas"):
+            with _blas_ctl.limit(limits=int(os.environ.get("CLEORA_B200_EIGH_THREADS", "1")), user_api="blas"):
                 vals, vecs = np.linalg.eigh(a)
         else:
             vals, vecs = np.linalg.eigh(a)

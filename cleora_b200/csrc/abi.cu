@@ -243,10 +243,13 @@ void transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T) {
     std::vector<double> a(cov, cov + d * d), w((size_t)d);
     int rc = g_eigh ? g_eigh(a.data(), w.data(), d, g_eigh_user) : eigh_cusolver(a.data(), w.data(), d, nullptr);
     if (rc != 0) throw std::runtime_error("eigh failed with code " + std::to_string(rc));
-    for (int64_t k = 0; k < dout; ++k) {
-        const int64_t src = d - 1 - k;                          // argsort(eigenvalues)[::-1] on ascending input
-        const double scale = 1.0 / std::sqrt(std::max(w[(size_t)src], 1e-10));
-        for (int64_t i = 0; i < d; ++i) T[i * dout + k] = (float)(a[(size_t)(i * d + src)] * scale);
+    std::vector<double> scale((size_t)dout);
+    for (int64_t k = 0; k < dout; ++k)                          // argsort(eigenvalues)[::-1] on ascending input: column d-1-k
+        scale[(size_t)k] = 1.0 / std::sqrt(std::max(w[(size_t)(d - 1 - k)], 1e-10));
+    for (int64_t i = 0; i < d; ++i) {
+        const double *row = a.data() + i * d + (d - 1);
+        float *t = T + i * dout;
+        for (int64_t k = 0; k < dout; ++k) t[k] = (float)(row[-k] * scale[(size_t)k]);
     }
 }
 
@@ -286,11 +289,34 @@ struct DeviceEigh {
     ~DeviceEigh() { if (h) cusolverDnDestroy(h); }
 };
 
+// Page-locked host staging (the covariance down / the transform up, once per iteration with a host eigensolver).
+template <typename T>
+struct PinnedBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    void resize(size_t count) {
+        if (count == n) return;
+        release();
+        if (count) CUDA_TRY(cudaHostAlloc((void **)&p, count * sizeof(T), cudaHostAllocDefault));
+        n = count;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+    }
+    T *data() { return p; }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+
 struct WhitenState {
     DevBuf<double> sums, cov;
     DevBuf<float> mean32, T;
-    std::vector<double> h_cov;
-    std::vector<float> h_T;
+    PinnedBuf<double> h_cov;
+    PinnedBuf<float> h_T;
     DeviceEigh eig;
     int64_t d = 0, dout = 0;
     void ensure(int64_t d_, int64_t dout_) {
@@ -375,6 +401,7 @@ struct Persistent {
         for (auto &b : buf) b.free();
         ws.sums.free(); ws.cov.free(); ws.mean32.free(); ws.T.free();
         ws.eig.evec.free(); ws.eig.eval.free(); ws.eig.work.free(); ws.eig.info.free();
+        ws.h_cov.release(); ws.h_T.release();
         ws.d = ws.dout = 0; ws.eig.d = 0;
     }
 };

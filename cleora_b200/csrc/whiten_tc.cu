@@ -6,14 +6,16 @@
 // miss its 1e-5 bar.
 //
 // Shape: one CTA = 128 rows of x (UMMA M = 128), all N <= 256 output columns (UMMA N = N), K = d in chunks of 32.
-// Warp roles (320 threads, persistent over row tiles):
+// Warp roles (352 threads, persistent over row tiles):
 //   warps 0-3  A producers: thread = row; 128-bit loads of 32 floats, centre, split hi/lo, 16-byte stores into the
 //              canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices, LBO 128 B, SBO 1024 B);
-//   warps 4-7  epilogue: tcgen05.ld of the warp's 32 TMEM lanes (thread = row), optional row L2 norm, global stores;
-//   warp  8    MMA issuer (one elected lane): 3 x 4 tcgen05.mma per K chunk, tcgen05.commit to free smem stages and to
-//              publish the accumulator;
-//   warp  9    B loader: the transform, pre-split and pre-tiled in global memory by prep_transform_kernel, is copied
-//              chunk by chunk with cp.async.bulk (TMA 1-D) signalling an mbarrier.
+//   warps 4-7  epilogue: tcgen05.ld of the warp's 32 TMEM lanes (thread = row), optional row L2 norm, global stores
+//              (and, when asked, the same stores into the peers' copies);
+//   warp  8    TMEM allocation + MMA issuer (one elected lane): 3 x 4 tcgen05.mma per K chunk, tcgen05.commit to free
+//              smem stages and to publish the accumulator;
+//   warps 9-10 B loaders: the transform, pre-split and pre-tiled in global memory by prep_transform_kernel, is copied
+//              chunk by chunk with 16-byte cp.async (LDGSTS) arriving on an mbarrier (cp.async.bulk was tried first
+//              and sustained only ~15 B/clk per SM here).
 // TMEM holds two accumulator buffers (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "device.cuh"
 #include "../../include/cleora_b200.h"
@@ -40,9 +42,6 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 // Waiting must be cheap: a warp that polls flat out steals issue slots from the producer warps on its scheduler
 // (measured: 6.7k warp-instructions per stage per SM, 80 % of them polling).  After the first failed probe the
 // waiter backs off with nanosleep (`sleep_ns`: ~32 for pipeline hand-offs, ~1000 for the rare accumulator drains).
@@ -64,11 +63,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
             else if (clock64() - t0 > 8000000000LL) __trap();
         }
     }
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 // 16-byte LDGSTS for the B operand: the 1-D bulk engine (cp.async.bulk / UBLKCP) sustained only ~15 B/clk per SM on
 // these 64 KB chunks and was the stage-time limiter (measured); LDGSTS from two warps is several times faster.
