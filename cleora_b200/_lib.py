@@ -66,6 +66,7 @@ PROTOTYPES = {
     "cleora_embed": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_double,
                                C.c_int, C.c_int, c_f32p, c_i64p, c_f64p]),
     "cleora_set_eigh": (None, [EIGH_FN, C.c_void_p]),
+    "cleora_set_eigh_thread": (None, [C.c_int, EIGH_FN, C.c_void_p]),
     "cleora_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
     "cleora_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "cleora_host_free": (None, [C.c_void_p]),
@@ -186,12 +187,12 @@ class host_eigh:
 
     def __enter__(self):
         if self.enable:
-            lib().cleora_set_eigh(_eigh_keepalive, None)
+            lib().cleora_set_eigh_thread(1, _eigh_keepalive, None)
         return self
 
     def __exit__(self, *exc):
         if self.enable:
-            lib().cleora_set_eigh(C.cast(None, EIGH_FN), None)
+            lib().cleora_set_eigh_thread(0, C.cast(None, EIGH_FN), None)
         return False
 
 

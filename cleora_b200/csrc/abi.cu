@@ -204,8 +204,20 @@ void check_norm(int norm) {
 }
 
 // ------------------------------------------------------------------------------------------------ eigh
-cleora_eigh_fn g_eigh = nullptr;
-void *g_eigh_user = nullptr;
+// Host eigensolver: a process-wide setting (cleora_set_eigh) and a per-thread override (cleora_set_eigh_thread) that
+// bindings use to scope a choice to one call without racing other threads.
+struct EighChoice {
+    cleora_eigh_fn fn = nullptr;
+    void *user = nullptr;
+};
+std::atomic<cleora_eigh_fn> g_eigh_fn{nullptr};
+std::atomic<void *> g_eigh_user{nullptr};
+thread_local int t_eigh_mode = 0;          // 0: follow the process-wide setting, 1: use t_eigh
+thread_local EighChoice t_eigh;
+EighChoice current_eigh() {
+    if (t_eigh_mode) return t_eigh;
+    return EighChoice{g_eigh_fn.load(), g_eigh_user.load()};
+}
 
 // Default eigensolver: cuSOLVER Dsyevd on the current device (a library call for the small d x d step; the
 // reference's own GPU path does the same through torch.linalg.eigh, pycleora/__init__.py:990).
@@ -241,7 +253,8 @@ int eigh_cusolver(double *a, double *w, int64_t d, void *) {
 // pycleora/__init__.py:145-156: eigh -> descending order -> scale = 1/sqrt(max(lambda,1e-10)) -> (V*scale) as f32.
 void transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T) {
     std::vector<double> a(cov, cov + d * d), w((size_t)d);
-    int rc = g_eigh ? g_eigh(a.data(), w.data(), d, g_eigh_user) : eigh_cusolver(a.data(), w.data(), d, nullptr);
+    const EighChoice eh = current_eigh();
+    int rc = eh.fn ? eh.fn(a.data(), w.data(), d, eh.user) : eigh_cusolver(a.data(), w.data(), d, nullptr);
     if (rc != 0) throw std::runtime_error("eigh failed with code " + std::to_string(rc));
     std::vector<double> scale((size_t)dout);
     for (int64_t k = 0; k < dout; ++k)                          // argsort(eigenvalues)[::-1] on ascending input: column d-1-k
@@ -374,7 +387,7 @@ void whiten_device(const float *Y, int64_t n, int64_t d, int64_t dout, float *Z,
     launch_f64_to_f32(ws.sums.p, ws.mean32.p, d, st);                    // mean.astype(float32)
     ph.end(PH_STATS);
     ph.begin();
-    if (g_eigh) {            // host eigensolver installed by the binding (e.g. numpy's LAPACK): one round trip
+    if (current_eigh().fn) {            // host eigensolver installed by the binding (e.g. numpy's LAPACK): one round trip
         CUDA_TRY(cudaMemcpyAsync(ws.h_cov.data(), ws.cov.p, sizeof(double) * d * d, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         transform_from_cov(ws.h_cov.data(), d, dout, ws.h_T.data());
@@ -478,7 +491,7 @@ void embed_pipelined(DeviceGraph &dg, const float *val, int markov, float *cur, 
     ph.begin();
     stats_device(y, n, d, ws, A);
     ph.end(PH_STATS);
-    const bool host_eigh = g_eigh != nullptr;       // e.g. numpy's LAPACK: runs on the CPU while the GPU does the SpMM
+    const bool host_eigh = current_eigh().fn != nullptr;       // e.g. numpy's LAPACK: runs on the CPU while the GPU does the SpMM
     for (int64_t it = 1; it < iters; ++it) {
         CUDA_TRY(cudaEventRecord(B.stats_done, A));
         CUDA_TRY(cudaStreamWaitEvent(B.s, B.stats_done, 0));
@@ -546,7 +559,11 @@ extern "C" int cleora_set_device(int device) {
     return guarded([&] { require_device(); CUDA_TRY(cudaSetDevice(device)); });
 }
 extern "C" uint64_t cleora_hash_entity(const char *bytes, int64_t len) { return xxh64(bytes, (size_t)len, 0); }
-extern "C" void cleora_set_eigh(cleora_eigh_fn fn, void *user) { g_eigh = fn; g_eigh_user = user; }
+extern "C" void cleora_set_eigh(cleora_eigh_fn fn, void *user) { g_eigh_user.store(user); g_eigh_fn.store(fn); }
+extern "C" void cleora_set_eigh_thread(int mode, cleora_eigh_fn fn, void *user) {
+    t_eigh_mode = mode ? 1 : 0;
+    t_eigh = EighChoice{mode ? fn : nullptr, mode ? user : nullptr};
+}
 extern "C" int cleora_set_option(const char *key, int64_t value) {
     return guarded([&] {
         const std::string k = key ? key : "";
@@ -821,7 +838,7 @@ extern "C" int cleora_dev_whiten_transform(const double *cov, int64_t d, int64_t
     return guarded([&] {
         if (dout <= 0 || dout > d) value_error("n_components must be in [1, d]");
         cudaStream_t st = (cudaStream_t)stream;
-        if (g_eigh) {
+        if (current_eigh().fn) {
             std::vector<double> h((size_t)d * d);
             std::vector<float> hT((size_t)d * dout);
             CUDA_TRY(cudaMemcpyAsync(h.data(), cov, sizeof(double) * d * d, cudaMemcpyDeviceToHost, st));

@@ -447,8 +447,8 @@ void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double 
     slices = (n + rows_per_slice - 1) / rows_per_slice;
     const int PS = 2;
     const size_t smem = (size_t)PS * 4 * ROWS * d + (size_t)RAW_STAGES * ROWS * (d * 4 + RAW_PAD) + (4 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
-    static bool attr = false;
-    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    // per device, not per process: set on every launch (a host-side table write)
+    CUDA_TRY(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     dim3 grid((unsigned)stripes, (unsigned)slices);
     gram_i8_kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, qp, m_int, G, colsum, rows_per_slice, PS);
     LAUNCH_CHECK();

@@ -730,8 +730,7 @@ void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *me
     static const bool use_v3 = [] { const char *e = getenv("CLEORA_B200_GRAM"); return !(e && std::string(e) == "v2"); }();
     if (use_v3 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
         const size_t smem = (size_t)G3_STAGES * 2 * GK * G3_LD * sizeof(float);      // 69,632 B
-        static bool attr = false;
-        if (!attr) { CUDA_TRY(cudaFuncSetAttribute(gram_f64_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        CUDA_TRY(cudaFuncSetAttribute(gram_f64_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
         gram_f64_v3_kernel<<<grid, 512, smem, st>>>(x, n, (int)d, mean, partial, nblk, rows_per_slice);
     } else if (d % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
         gram_f64_kernel<true><<<grid, 512, 0, st>>>(x, n, (int)d, mean, partial, nblk, rows_per_slice);

@@ -142,7 +142,10 @@ int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64_t iters, i
  * success.  Default (NULL): cuSOLVER Dsyevd on the device, enqueued on the loop's stream (no host sync).  Set
  * CLEORA_B200_EIGH=numpy to make the Python binding install numpy's LAPACK eigh, the call the reference makes. */
 typedef int (*cleora_eigh_fn)(double *a, double *w, int64_t d, void *user);
-void cleora_set_eigh(cleora_eigh_fn fn, void *user);
+void cleora_set_eigh(cleora_eigh_fn fn, void *user);            /* process-wide */
+/* Override for the calling thread only (takes precedence over cleora_set_eigh): mode 1 = use `fn` (NULL = cuSOLVER),
+ * mode 0 = follow the process-wide setting again.  Lets a binding scope an eigensolver to one call. */
+void cleora_set_eigh_thread(int mode, cleora_eigh_fn fn, void *user);
 
 /* Tuning switches.  "pipeline_whiten" (default 1): in cleora_embed's default configuration (whiten, l2, no residual,
  * no early stop, d % 32 == 0, d <= 256) overlap the eigensolve with the next SpMM using
