@@ -243,7 +243,7 @@ def run_ours(args, w, name):
         if i > 0:
             e2e_times.append(time.perf_counter() - t0)
     e2e_t = sum(e2e_times) / len(e2e_times)
-    h2d = 8 * (n + 1) + nnz * (4 + 4 + 4) + 8 * n                       # rowptr + col + left + sym + hashes
+    h2d = 8 * (n + 1) + nnz * (4 + 4) + 8 * n     # rowptr + col + left values + hashes (sym values only on first symmetric use)
     d2h = 4 * n * d
 
     # ---- roofline of the dominant kernel (K1 SpMM+L2), live CUDA-event time from the same timed region

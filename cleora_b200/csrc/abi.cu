@@ -144,11 +144,7 @@ DeviceGraph &device_graph(Graph &g) {
         CUDA_TRY(cudaMalloc((void **)&dg->left, (nnz + pad) * sizeof(float)));
         CUDA_TRY(cudaMemset(dg->left, 0, (nnz + pad) * sizeof(float)));
         CUDA_TRY(cudaMemcpy(dg->left, g.left.data(), nnz * sizeof(float), cudaMemcpyHostToDevice));
-        if (!g.sym.empty()) {
-            CUDA_TRY(cudaMalloc((void **)&dg->sym, (nnz + pad) * sizeof(float)));
-            CUDA_TRY(cudaMemset(dg->sym, 0, (nnz + pad) * sizeof(float)));
-            CUDA_TRY(cudaMemcpy(dg->sym, g.sym.data(), nnz * sizeof(float), cudaMemcpyHostToDevice));
-        }
+        if (!g.sym.empty()) dg->host_sym = g.sym.data();       // uploaded by values_of() when first asked for
         if (!g.hash.empty()) {
             CUDA_TRY(cudaMalloc((void **)&dg->hash, g.hash.size() * sizeof(uint64_t)));
             CUDA_TRY(cudaMemcpy(dg->hash, g.hash.data(), g.hash.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
@@ -190,10 +186,21 @@ DeviceGraph &device_graph(Graph &g) {
     return *dg;
 }
 
-const float *values_of(const DeviceGraph &dg, int markov) {
+const float *values_of(DeviceGraph &dg, int markov) {
     if (markov == CLEORA_MARKOV_LEFT) return dg.left;
     if (markov == CLEORA_MARKOV_SYMMETRIC) {
-        if (!dg.sym) value_error("graph was created without symmetric Markov values");
+        if (!dg.sym) {
+            if (!dg.host_sym) value_error("graph was created without symmetric Markov values");
+            const size_t pad = 16, nnz = (size_t)dg.nnz;
+            float *p = nullptr;
+            CUDA_TRY(cudaMalloc((void **)&p, (nnz + pad) * sizeof(float)));
+            if (cudaMemset(p, 0, (nnz + pad) * sizeof(float)) != cudaSuccess ||
+                cudaMemcpy(p, dg.host_sym, nnz * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+                cudaFree(p);
+                throw CudaFail{std::string("upload of symmetric values failed: ") + cudaGetErrorString(cudaGetLastError())};
+            }
+            dg.sym = p;
+        }
         return dg.sym;
     }
     value_error("Unknown propagation. Use 'left' or 'symmetric'.");

@@ -17,6 +17,7 @@ struct DeviceGraph {
     int64_t *rowptr = nullptr;
     uint32_t *col = nullptr;
     float *left = nullptr, *sym = nullptr;
+    const float *host_sym = nullptr;       // symmetric values are uploaded on first use (the default loop never reads them)
     uint64_t *hash = nullptr;
     // long-row schedule: rows with more than long_threshold edges are split into chunks of long_chunk_edges, one warp
     // per chunk (kernels.cu); built at upload time

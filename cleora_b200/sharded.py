@@ -637,7 +637,7 @@ def bench(args, w, name, gen_pairs, spmm_bytes, measured_peaks, ClockSampler):
                        "l2_flush": "inputs exceed the 126 MB L2"},
             "nnz_per_s": nnz * iters / (ms_step * 1e-3),
             "e2e": {"value": E * iters / float(e2e.item()), "unit": "edges/s",
-                    "h2d_bytes_per_step": int(8 * (shard.n_local + 1) + 12 * shard.nnz_local + 8 * n),
+                    "h2d_bytes_per_step": int(8 * (shard.n_local + 1) + 8 * shard.nnz_local + 8 * n),
                     "d2h_bytes_per_step": int(4 * shard.n_local * d), "ms_per_step": 1e3 * float(e2e.item()),
                     "note": "per-rank bytes; each rank uploads its CSR shard and downloads its own rows of the result"},
             "gpu_launches": int(launches.item()),
