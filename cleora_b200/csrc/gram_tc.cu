@@ -15,17 +15,19 @@
 // typical element).  Integer accumulation is order-independent, so the result is bit-identical for any slicing,
 // any atomic order and any GPU count.
 //
-// One CTA = a 128 x 64 output tile (row block i, column stripe j) for a slice of rows: TMEM holds the 7 weight-group
-// accumulators of 128 x 64 int32 = 448 of its 512 columns.  Per 32-row stage: 4 loader warps stage the rows (cp.async,
-// 4 stages deep), 8 converter warps quantise all d columns into four byte planes in the canonical MN-major
-// no-swizzle UMMA layout (8 K-rows x 16 bytes per core matrix), one lane issues the 16 tcgen05.mma (both operands are
-// views of the planes: A = the 128 columns of block i in plane k, B = the stripe's 64 columns in plane l), and 4
-// drain warps move the accumulators to int64 global memory every 192 stages.
+// One CTA = a 128 x 64 output tile (row block i, column stripe j at or right of block i -- every G_s is symmetric, the
+// combine kernel mirrors the rest) for a slice of rows: TMEM holds the 7 weight-group accumulators of 128 x 64 int32 =
+// 448 of its 512 columns.  Per 32-row stage: 4 loader warps stage the rows (cp.async, 4 stages deep), 8 converter warps
+// quantise all d columns into four byte planes in a canonical no-swizzle UMMA layout (MN-major for d = 256, K-major
+// for d = 128), one lane issues the 16 tcgen05.mma (both operands are views of the planes: A = the 128 columns of block
+// i in plane k, B = the stripe's 64 columns in plane l), and 4 drain warps move the accumulators to int64 global memory
+// every 192 stages.
 #include "device.cuh"
 #include "../../include/cleora_b200.h"
 
 #include <algorithm>
 #include <cstdlib>
+#include <string>
 
 namespace cleora {
 namespace g8 {
@@ -36,9 +38,11 @@ constexpr int RAW_PAD = 16;        // raw f32 rows are staged with a 16-byte ske
 constexpr int STRIPE = 64;         // output columns per CTA (UMMA N); the CTA owns ONE 128-row block i x this stripe
 constexpr int GROUPS = 7;          // weight groups s = k + l
 constexpr int DRAIN_STAGES = 192;  // 192*32 = 6144 rows: 4 * 255^2 * 6144 < 2^31
-constexpr int CONV_THREADS = 256;  // 8 converter warps
+constexpr int CONV_THREADS = 256;  // 8 converter warps (16 were tried with the K-major converter: +7 % only)
 constexpr int LOAD_THREADS = 128;  // 4 loader warps (cp.async, fully coalesced)
 constexpr int THREADS = CONV_THREADS + 128 + 32 + LOAD_THREADS;   // + 4 drain warps + MMA warp + loaders
+constexpr int PS = 2;              // plane stages; compile-time, like RAW_STAGES: a runtime modulo in the per-stage
+                                   // bookkeeping cost every role ~10 % (measured 2.10 -> 1.88 ms)
 constexpr int RAW_STAGES = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,9 +94,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-// kind::i8 instruction descriptor: D = s32 (2), A/B format 0 = u8 / 1 = s8, both MN-major, M = 128, N = 32.
-__device__ __forceinline__ uint32_t make_idesc_i8(int a_signed, int b_signed) {
-    return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | (1u << 15) | (1u << 16) |
+// kind::i8 instruction descriptor: D = s32 (2), A/B format 0 = u8 / 1 = s8, both operands MN-major (bits 15/16 set)
+// or both K-major, M = 128, N = STRIPE.
+__device__ __forceinline__ uint32_t make_idesc_i8(int a_signed, int b_signed, bool mn_major) {
+    return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) |
            ((uint32_t)(STRIPE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -171,10 +176,16 @@ __global__ void quant_params_kernel(const float *__restrict__ absmax_partial, in
     for (int j = threadIdx.x; j < d; j += blockDim.x) m_int[j] = (int32_t)llrint(mean[j] * (double)s_scale);
 }
 
+// KMAJOR selects the shared-memory layout of the byte planes (both are canonical no-swizzle UMMA layouts):
+//   false: MN-major -- core matrix = 8 rows (K) x 16 columns (MN); a converter thread owns 16 columns of one row;
+//   true : K-major  -- core matrix = 8 columns (MN) x 16 rows (K); a converter thread owns one column of 16 rows.
+// Measured (n = 1M, d = 256 / n = 300k, d = 128): MN-major 1.88 / 0.30 ms, K-major 2.29 / 0.24 ms -- the launcher
+// picks MN-major for d = 256 and K-major for d = 128 (where the MN-major mapping leaves half the converters idle).
+template <bool KMAJOR>
 __global__ void __launch_bounds__(g8::THREADS, 1)
 gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantParams *__restrict__ qp,
                const int32_t *__restrict__ m_int, long long *__restrict__ G /* [7][d][d] */,
-               long long *__restrict__ colsum /* [d] */, int64_t rows_per_slice, int PS /* plane stages */) {
+               long long *__restrict__ colsum /* [d] */, int64_t rows_per_slice) {
     using namespace g8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int plane_bytes = ROWS * d;                                 // one byte plane of one stage
@@ -228,6 +239,61 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < CONV_WARPS) {
+      if constexpr (KMAJOR) {
+        // ------------------------------------------------------------ converters, K-major planes
+        // item = (column j, 16-row K chunk kc); thread t owns items t, t + 256, ...  (d = 256: column t, both chunks;
+        // d = 128: column t % 128, chunk t / 128).  A warp reads 32 consecutive floats of one raw row (conflict-free
+        // LDS.32) and stores 32 x 16 bytes = four adjacent core matrices per plane (conflict-free STS.128).
+        // Plane byte offset of (j, r) = (j / 8) * 256 + (r / 16) * 128 + (j % 8) * 16 + r % 16.
+        const float scale = qp->scale;
+        const int total_items = d * (ROWS / 16);                        // (column, 16-row chunk) pairs per stage
+        const int n_items = (total_items + CONV_THREADS - 1) / CONV_THREADS;
+        long long csum = 0;                                             // all of a thread's items share one column
+        const int j = threadIdx.x % d;
+        const int mi = __ldg(m_int + j);
+        for (int st = 0; st < n_stages; ++st) {
+            const int rs = st % RAW_STAGES, s = st % PS;
+            mbar_wait(&raw_full[rs], (st / RAW_STAGES) & 1);
+            mbar_wait(&empty[s], ((st / PS) & 1) ^ 1);
+            const unsigned char *raw = sR + rs * raw_bytes;
+            unsigned char *base = sP + s * stage_bytes;
+            const int64_t row0 = r0 + (int64_t)st * ROWS;
+            for (int it = 0; it < n_items; ++it) {
+                if ((int)threadIdx.x + it * CONV_THREADS >= total_items) break;   // spare threads only keep the barriers' counts
+                const int kc = (threadIdx.x + it * CONV_THREADS) / d;
+                int qv[16];
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr) {
+                    const int r = kc * 16 + rr;
+                    const float v = *reinterpret_cast<const float *>(raw + r * raw_stride + j * 4);
+                    qv[rr] = (row0 + r < r1) ? __float2int_rn(v * scale) - mi : 0;
+                }
+                uint4 pl[4];
+#pragma unroll
+                for (int wq = 0; wq < 4; ++wq) {
+                    const uint32_t a = (uint32_t)qv[4 * wq], b2 = (uint32_t)qv[4 * wq + 1];
+                    const uint32_t c2 = (uint32_t)qv[4 * wq + 2], d2 = (uint32_t)qv[4 * wq + 3];
+                    const uint32_t t0 = __byte_perm(a, b2, 0x5140), t1 = __byte_perm(a, b2, 0x7362);
+                    const uint32_t t2 = __byte_perm(c2, d2, 0x5140), t3 = __byte_perm(c2, d2, 0x7362);
+                    (&pl[0].x)[wq] = __byte_perm(t0, t2, 0x5410);
+                    (&pl[1].x)[wq] = __byte_perm(t0, t2, 0x7632);
+                    (&pl[2].x)[wq] = __byte_perm(t1, t3, 0x5410);
+                    (&pl[3].x)[wq] = __byte_perm(t1, t3, 0x7632);
+                }
+                const uint32_t off = (uint32_t)((j >> 3) * 256 + kc * 128 + (j & 7) * 16);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) *reinterpret_cast<uint4 *>(base + p * plane_bytes + off) = pl[p];
+                if (owns_colsum) {
+#pragma unroll
+                    for (int rr = 0; rr < 16; ++rr) csum += qv[rr];
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&full[s]);
+            mbar_arrive(&raw_empty[rs]);
+        }
+        if (owns_colsum && csum != 0) atomicAdd(reinterpret_cast<unsigned long long *>(colsum + j), (unsigned long long)csum);
+      } else {
         // ------------------------------------------------------------ converters: raw f32 (smem) -> 4 byte planes
         // thread -> (row lane rl = tid % 8, column group cg = (tid / 8) % 16, half h = tid / 128); it converts rows
         // rl + 8*i, i in {2h, 2h+1}.  A quarter-warp = 8 consecutive rows of one column group = one 128-byte core matrix
@@ -300,6 +366,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             for (int c = 0; c < 16; ++c)
                 if (csum[c] != 0) atomicAdd(reinterpret_cast<unsigned long long *>(colsum + cg * 16 + c), (unsigned long long)csum[c]);
         }
+      }
     } else if (warp < CONV_WARPS + 4) {
         // ------------------------------------------------------------ drain: TMEM int32 -> global int64 (atomic)
         const int q4 = warp - CONV_WARPS;
@@ -326,7 +393,11 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     } else if (warp == CONV_WARPS + 4) {
         // ------------------------------------------------------------ MMA issuer
         int drains = 0;
-        const uint32_t lbo = 128, sbo = (ROWS / 8) * 128;             // K groups adjacent, MN groups 512 B apart
+        // MN-major: LBO = step between 8-row K groups (128 B), SBO = step between 16-column MN groups (512 B);
+        // K-major: LBO = step between 16-row K chunks (128 B), SBO = step between 8-column MN groups (256 B).
+        const uint32_t lbo = 128, sbo = KMAJOR ? (ROWS / 16) * 128 : (ROWS / 8) * 128;
+        const uint32_t a_off = KMAJOR ? (uint32_t)(mb * 16) * sbo : (uint32_t)(mb * 8) * sbo;        // first MN group of block i
+        const uint32_t b_off = KMAJOR ? (uint32_t)(js * (STRIPE / 8)) * sbo : (uint32_t)(js * (STRIPE / 16)) * sbo;
         for (int st = 0; st < n_stages; ++st) {
             const int s = st % PS;
             const bool first = (st % DRAIN_STAGES) == 0;              // first stage after a drain: overwrite
@@ -341,14 +412,14 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
                 uint32_t used = 0;                                    // bit g: accumulator already written this stage
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint64_t ad = make_desc(pbase + k * plane_bytes + (mb * 8) * sbo, lbo, sbo);
+                    const uint64_t ad = make_desc(pbase + k * plane_bytes + a_off, lbo, sbo);
 #pragma unroll
                     for (int l = 0; l < 4; ++l) {
-                        const uint64_t bd = make_desc(pbase + l * plane_bytes + (js * (STRIPE / 16)) * sbo, lbo, sbo);
+                        const uint64_t bd = make_desc(pbase + l * plane_bytes + b_off, lbo, sbo);
                         const int g = k + l;
                         const uint32_t acc = (first && !(used & (1u << g))) ? 0u : 1u;
                         used |= 1u << g;
-                        mma_i8(tmem_base + (uint32_t)(g * STRIPE), ad, bd, make_idesc_i8(k == 3, l == 3), acc);
+                        mma_i8(tmem_base + (uint32_t)(g * STRIPE), ad, bd, make_idesc_i8(k == 3, l == 3, !KMAJOR), acc);
                     }
                 }
                 mma_commit(&empty[s]);
@@ -445,12 +516,20 @@ void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double 
     int64_t slices = std::max<int64_t>(1, std::min<int64_t>(148 / stripes, (n + 4 * ROWS - 1) / (4 * ROWS)));   // one wave
     const int64_t rows_per_slice = ((n + slices - 1) / slices + ROWS - 1) / ROWS * ROWS;
     slices = (n + rows_per_slice - 1) / rows_per_slice;
-    const int PS = 2;
     const size_t smem = (size_t)PS * 4 * ROWS * d + (size_t)RAW_STAGES * ROWS * (d * 4 + RAW_PAD) + (4 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
+    // plane layout: CLEORA_B200_GRAM_LAYOUT=mn|k overrides the per-shape default (see the kernel's comment)
+    static const int forced = [] {
+        const char *e = getenv("CLEORA_B200_GRAM_LAYOUT");
+        const std::string v = e ? e : "";
+        return v == "mn" ? 0 : v == "k" ? 1 : -1;
+    }();
+    const bool kmajor = forced >= 0 ? forced == 1 : d < 256;
+    auto kernel = kmajor ? gram_i8_kernel<true> : gram_i8_kernel<false>;
+    const int threads = THREADS;
     // per device, not per process: set on every launch (a host-side table write)
-    CUDA_TRY(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     dim3 grid((unsigned)stripes, (unsigned)slices);
-    gram_i8_kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, qp, m_int, G, colsum, rows_per_slice, PS);
+    kernel<<<grid, threads, smem, st>>>(x, n, (int)d, qp, m_int, G, colsum, rows_per_slice);
     LAUNCH_CHECK();
     gram_i8_combine_kernel<<<(unsigned)((d * d + 255) / 256), 256, 0, st>>>(G, colsum, m_int, mean, (int)d, n, qp, cov);
     LAUNCH_CHECK();
