@@ -376,17 +376,20 @@ void launch_normalize(const float *x, int64_t n, int64_t d, int norm, float *out
 }
 
 // ================================================================================================ K2a column sums
-// Stage 1: every warp of the grid walks rows warp, warp+W, ... and keeps f64 partial sums of its columns
-// (lane owns columns lane, lane+32, ...).  Stage 2: one thread per column adds the W partials in warp order.
+// Stage 1: every warp of the grid walks rows warp, warp+W, ... and keeps f64 partial sums of its columns (lane owns
+// columns lane, lane+32, ...); the 8 warps of a block then add their partials through shared memory in warp order,
+// one partial row per block.  Stage 2: one thread per column adds the block partials in block order.
 // Deterministic for a fixed launch shape.
 // `absmax` (nullable, one float per block): max |x| over the elements this block read -- free here, and it saves the
 // integer Gram kernel a pass of its own.
 template <int T>
 __global__ void __launch_bounds__(256) col_sums_stage1(const float *__restrict__ x, int64_t n, int d, int c0,
                                                        double *__restrict__ partial, float *__restrict__ absmax) {
-    const int lane = threadIdx.x & 31;
+    __shared__ double sh_acc[8][T * 32];
+    __shared__ float sh_mx[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t W = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     double acc[T];
     float mx = 0.f;
 #pragma unroll
@@ -402,17 +405,21 @@ __global__ void __launch_bounds__(256) col_sums_stage1(const float *__restrict__
             }
     }
 #pragma unroll
-    for (int t = 0; t < T; ++t)
-        if (c0 + t * 32 + lane < d) partial[w * d + c0 + t * 32 + lane] = acc[t];
-    if (absmax != nullptr) {                                   // uniform branch; all 8 warps reach the barrier
-        __shared__ float sh_mx[8];
-        for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-        if (lane == 0) sh_mx[threadIdx.x >> 5] = mx;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int q = 1; q < 8; ++q) mx = fmaxf(mx, sh_mx[q]);
-            absmax[blockIdx.x] = mx;
+    for (int t = 0; t < T; ++t) sh_acc[wib][t * 32 + lane] = acc[t];
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if (lane == 0) sh_mx[wib] = mx;
+    __syncthreads();
+    for (int c = threadIdx.x; c < T * 32; c += blockDim.x)
+        if (c0 + c < d) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s += sh_acc[q][c];
+            partial[(int64_t)blockIdx.x * d + c0 + c] = s;
         }
+    if (absmax != nullptr && threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 1; q < 8; ++q) mx = fmaxf(mx, sh_mx[q]);
+        absmax[blockIdx.x] = mx;
     }
 }
 
@@ -443,7 +450,7 @@ void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool ac
     const int threads = 256;
     int64_t blocks = std::min<int64_t>((n + 7) / 8, 148 * 4);
     if (blocks < 1) blocks = 1;
-    const int64_t W = blocks * (threads / 32);
+    const int64_t W = blocks;                                  // one partial row per block
     double *partial = (double *)workspace().colsum_partials.get(size_t(W) * size_t(d) * sizeof(double));
     float *mx = nullptr;
     if (absmax && d <= 8 * 32 && n > 0) {                      // one column pass covers the whole matrix
