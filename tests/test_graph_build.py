@@ -145,3 +145,46 @@ def test_entity_ids_setter_rehashes():
     assert g.entity_ids == ["x", "yy"]
     np.testing.assert_array_equal(g.entity_hashes(), [oracle.xxh64(b"x"), oracle.xxh64(b"yy")])
     assert g.get_entity_index("yy") == 1
+
+
+# ------------------------------------------------------------------------------------------------ differential fuzz
+from hypothesis import given, settings, HealthCheck  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+_TOKEN = st.sampled_from(["a", "b", "c", "d", "e", "f", "g", "h", "x1", "x2", "é", "0", "00", "A", "a "])
+_CELL = st.lists(_TOKEN, min_size=0, max_size=7).map(" ".join)
+_LINE = st.one_of(
+    _CELL,                                                        # one column
+    st.tuples(_CELL, _CELL).map("\t".join),                       # two columns, tab
+    st.tuples(_CELL, _CELL).map(",".join),                        # two columns, comma
+    st.tuples(_CELL, _CELL, _CELL).map("\t".join),                # wrong column count for every spec below
+    st.sampled_from(["", " ", "\t", ",", "a,,b", " a\tb ", "a \t b,c"]),
+)
+_SPEC = st.sampled_from(["complex::reflexive::n", "REFLEXIVE::Complex::n", "complex::u complex::p", "u complex::p",
+                         "complex::u p", "u p"])
+
+
+@settings(max_examples=200, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(lines=st.lists(_LINE, min_size=0, max_size=40), columns=_SPEC, trim=st.sampled_from([2, 3, 16]))
+def test_builder_differential_fuzz(lines, columns, trim):
+    """Two independent restatements of the reference's parser / indexer / clique expansion / trimming (C oracle,
+    C++ product) must agree bit for bit on arbitrary small inputs."""
+    try:
+        o = oracle.build_graph(lines, columns, trim)
+    except ValueError as e:
+        with pytest.raises(ValueError) as info:
+            cb.SparseMatrix.from_iterator(iter(lines), columns, hyperedge_trim_n=trim)
+        assert str(info.value) == str(e)
+        return
+    assert_same_graph(cb.SparseMatrix.from_iterator(iter(lines), columns, hyperedge_trim_n=trim), o)
+
+
+@settings(max_examples=200, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(pairs=st.lists(st.tuples(st.integers(0, 12), st.integers(0, 12)), min_size=0, max_size=60))
+def test_integer_ingest_differential_fuzz(pairs):
+    """from_edge_arrays(src, dst) == from_iterator over the lines "src dst" (duplicates, self pairs, gaps in the ids)."""
+    u = np.array([p[0] for p in pairs], np.uint32)
+    v = np.array([p[1] for p in pairs], np.uint32)
+    g = cb.SparseMatrix.from_edge_arrays(u, v, "node")
+    o = oracle.build_graph([f"{a} {b}" for a, b in pairs], "complex::reflexive::node", 16)
+    assert_same_graph(g, o)
