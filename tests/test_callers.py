@@ -48,6 +48,60 @@ def test_update_graph_keeps_first_appearance_order():
         np.testing.assert_array_equal(got, ref)
 
 
+@pytest.fixture
+def oracle_device(monkeypatch):
+    """Test double: the two device entry points the callers use are served by the CPU oracle, so their host logic
+    (feature blending, tap scheduling, warm-start row mapping, RNG use) is checked bit for bit without a GPU."""
+    import oracle
+    from cleora_b200 import _lib, callers
+    names = {v: k for k, v in cb._DEVICE_NORMS.items()}
+    graphs = {}
+
+    def og(sm):
+        return graphs[id(sm)]
+
+    real_from_iterator = cb.SparseMatrix.from_iterator
+
+    def from_iterator(lines, columns, hyperedge_trim_n=16, num_workers=None):
+        lines = list(lines)
+        sm = real_from_iterator(lines, columns, hyperedge_trim_n)
+        graphs[id(sm)] = oracle.build_graph(lines, columns, hyperedge_trim_n)
+        sm._keep = graphs                                    # keep ids stable for the test's lifetime
+        return sm
+
+    def embed_device(self, feature_dim, num_iterations, propagation="left", normalization=_lib.NORM_L2_NUMPY, seed=0,
+                     initial_embeddings=None, residual_weight=0.0, convergence_threshold=0.0, whiten=True, out=None,
+                     timings=None):
+        x = initial_embeddings if initial_embeddings is not None else oracle.init_matrix(og(self).hashes, feature_dim, seed)
+        res = oracle.embed(og(self), x.shape[1], num_iterations, propagation, names[normalization], seed, x, None,
+                           residual_weight, convergence_threshold, whiten)
+        return res, num_iterations
+
+    monkeypatch.setattr(cb.SparseMatrix, "from_iterator", staticmethod(from_iterator))
+    monkeypatch.setattr(callers.SparseMatrix, "from_iterator", staticmethod(from_iterator))
+    monkeypatch.setattr(cb.SparseMatrix, "embed_device", embed_device)
+    monkeypatch.setattr(cb.SparseMatrix, "initialize_deterministically",
+                        lambda self, d, seed=0: oracle.init_matrix(og(self).hashes, d, seed))
+    return cb
+
+
+def test_callers_host_logic_bit_exact_with_oracle_double(fx, oracle_device):
+    lines, cols = [str(s) for s in fx["lines"]], str(fx["columns"])
+    g = cb.SparseMatrix.from_iterator(lines, cols)
+    np.testing.assert_array_equal(cb.embed_multiscale(g, feature_dim=8, scales=[4, 2, 5]), fx["multiscale_w"])
+    np.testing.assert_array_equal(
+        cb.embed_multiscale(g, feature_dim=16, scales=[3, 9], whiten=False, propagation="symmetric"), fx["multiscale_now"])
+    feats = {str(k): v for k, v in zip(fx["feat_ids"], fx["feat_vals"])}
+    np.testing.assert_array_equal(cb.embed_with_node_features(g, feats, num_iterations=4, feature_weight=0.3),
+                                  fx["node_features"])
+    old, new = [str(s) for s in fx["old_lines"]], [str(s) for s in fx["new_lines"]]
+    g_old = cb.SparseMatrix.from_iterator(old, cols)
+    np.random.seed(int(fx["inductive_seed"]))
+    g_new, got = cb.embed_inductive(g_old, fx["trained"], old, new, cols, num_iterations=3)
+    assert g_new.entity_ids == [str(s) for s in fx["inductive_ids"]]
+    np.testing.assert_array_equal(got, fx["inductive"])
+
+
 # ------------------------------------------------------------------------------------------------ device parity
 @pytest.mark.gpu
 def test_multiscale_taps_whitened(fx):
