@@ -18,7 +18,7 @@ import pytest
 import cleora_b200 as cb
 import oracle
 from cleora_b200 import _lib
-from tests.helpers import KARATE_COLUMNS, KARATE_EDGES, er_lines, hyper_lines, scale_rel_err
+from tests.helpers import KARATE_COLUMNS, KARATE_EDGES, er_lines, scale_rel_err
 
 pytestmark = pytest.mark.gpu
 
