@@ -127,7 +127,7 @@ def embed(
     # Eigensolver choice (see _lib.eigh_mode): the rmse early stop on the whitened path compares successive iterates
     # element-wise, so it depends on the eigensolver's sign conventions -- such calls use the reference's own LAPACK
     # eigh; the pipelined default loop also uses it (on the host, hidden behind the SpMM); otherwise cuSOLVER.
-    lapack = whiten and convergence_threshold > 0
+    lapack = whiten and convergence_threshold > 0 and _lib.eigh_mode() != "cusolver"
     if callback is None:
         out, _ = graph.embed_device(feature_dim, num_iterations, propagation, _DEVICE_NORMS[normalization], seed,
                                     x0, residual_weight, convergence_threshold, whiten)
