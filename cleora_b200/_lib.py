@@ -68,6 +68,7 @@ PROTOTYPES = {
     "cleora_set_eigh": (None, [EIGH_FN, C.c_void_p]),
     "cleora_set_eigh_thread": (None, [C.c_int, EIGH_FN, C.c_void_p]),
     "cleora_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+    "cleora_get_option": (C.c_int64, [C.c_char_p]),
     "cleora_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "cleora_host_free": (None, [C.c_void_p]),
     "cleora_dev_graph_prepare": (C.c_int, [C.c_void_p]),
@@ -94,6 +95,7 @@ PROTOTYPES = {
     "cleora_whiten_apply_fusable": (C.c_int, [C.c_int64, C.c_int64]),
     "cleora_dev_sq_diff_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "cleora_dev_whiten_transform": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cleora_dev_chol_whiten": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cleora_whiten_transform_from_cov": (C.c_int, [c_f64p, C.c_int64, C.c_int64, c_f32p]),
     "cleora_release_workspace": (C.c_int, []),
     "cleora_dev_workspace_bytes": (C.c_int64, []),
@@ -154,29 +156,28 @@ def lib():
         L.cleora_set_eigh(_eigh_keepalive, None)
     if os.environ.get("CLEORA_B200_PIPELINE", "1") == "0":
         L.cleora_set_option(b"pipeline_whiten", 0)
+    if os.environ.get("CLEORA_B200_CHOL", "1") == "0":
+        L.cleora_set_option(b"chol_whiten", 0)
     _lib = L
     return L
 
 
 def eigh_mode() -> str:
     """CLEORA_B200_EIGH: "auto" (default), "numpy" (always the reference's LAPACK call, on the host) or "cusolver"
-    (always cuSOLVER Dsyevd on the device).  auto = LAPACK on the host where the loop can hide it behind the SpMM
-    (single-GPU pipelined loop: measured 400 vs 444 ms per C2 step) or where the reference's sign convention matters
-    (rmse early stop on whitened iterates); cuSOLVER everywhere else (multi-GPU ranks, standalone whitening)."""
+    (always cuSOLVER Dsyevd on the device).  The loop itself no longer needs an eigensolver per iteration (iterates
+    that stay inside the loop are whitened with the Cholesky factor on the device, see chol_whiten.cu); the choice
+    matters for the iterates that leave it.  auto = cuSOLVER, except where the reference's LAPACK sign convention
+    decides the outcome (rmse early stop on whitened iterates compares successive iterates element-wise)."""
     m = os.environ.get("CLEORA_B200_EIGH", "auto")
     return m if m in ("auto", "numpy", "cusolver") else "auto"
 
 
 def auto_host_eigh(n: int, d: int, iters: int, norm: int, whiten: bool, residual_weight: float,
                    convergence_threshold: float) -> bool:
-    """Would the default single-GPU loop run pipelined (abi.cu: pipeline_eligible) or need LAPACK's conventions?"""
+    """Does this call need LAPACK's conventions on the host (see eigh_mode)?"""
     if not whiten or eigh_mode() == "cusolver":
         return False
-    if convergence_threshold > 0:
-        return True
-    return (eigh_mode() == "auto" and n > 1 and iters >= 2 and norm == NORM_L2_NUMPY and residual_weight == 0
-            and os.environ.get("CLEORA_B200_PIPELINE", "1") != "0"
-            and bool(lib().cleora_whiten_apply_fusable(d, d)))
+    return convergence_threshold > 0
 
 
 class host_eigh:

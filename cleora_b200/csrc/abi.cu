@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -40,9 +41,16 @@ void Scratch::release() {
     p = nullptr;
     cap = 0;
 }
+static int current_device() {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    return dev;
+}
+// Scratch and cached state are per (host thread, device): a thread that switches devices (cleora_set_device) gets a
+// separate set instead of launching on buffers, streams or handles that belong to the previous device.
 Workspace &workspace() {
-    static thread_local Workspace ws;
-    return ws;
+    static thread_local std::map<int, Workspace> ws;
+    return ws[current_device()];
 }
 
 namespace {
@@ -118,10 +126,10 @@ void free_device_graph(DeviceGraph *dg) {
 // touch unmapped memory.
 DeviceGraph &device_graph(Graph &g) {
     require_device();
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (g.dev && g.dev->device != dev) { free_device_graph(g.dev); g.dev = nullptr; }
-    if (g.dev) return *g.dev;
+    const int dev = current_device();
+    std::lock_guard<std::recursive_mutex> lock(g.mu);
+    for (DeviceGraph *have : g.devs)
+        if (have->device == dev) return *have;
     if (!g.host_pinned && env_int64("CLEORA_B200_PIN_CSR", 1) != 0 && g.nnz() >= (1 << 20)) {
         // page-lock the host CSR once: uploads then run at PCIe speed instead of through the pageable staging path
         auto pin = [](const void *p, size_t bytes) { if (bytes) { if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) cudaGetLastError(); } };
@@ -182,13 +190,14 @@ DeviceGraph &device_graph(Graph &g) {
         free_device_graph(dg);
         throw;
     }
-    g.dev = dg;
+    g.devs.push_back(dg);
     return *dg;
 }
 
 const float *values_of(DeviceGraph &dg, int markov) {
     if (markov == CLEORA_MARKOV_LEFT) return dg.left;
     if (markov == CLEORA_MARKOV_SYMMETRIC) {
+        std::lock_guard<std::mutex> lock(dg.lazy_mu);
         if (!dg.sym) {
             if (!dg.host_sym) value_error("graph was created without symmetric Markov values");
             const size_t pad = 16, nnz = (size_t)dg.nnz;
@@ -229,7 +238,10 @@ EighChoice current_eigh() {
 // Default eigensolver: cuSOLVER Dsyevd on the current device (a library call for the small d x d step; the
 // reference's own GPU path does the same through torch.linalg.eigh, pycleora/__init__.py:990).
 int eigh_cusolver(double *a, double *w, int64_t d, void *) {
-    static thread_local cusolverDnHandle_t h = nullptr;
+    static thread_local std::map<int, cusolverDnHandle_t> handles;       // one per (thread, device)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    cusolverDnHandle_t &h = handles[dev];
     if (!h && cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) return 1;
     const int n = (int)d;
     int lwork = 0, info = 0;
@@ -337,13 +349,23 @@ struct WhitenState {
     DevBuf<float> mean32, T;
     PinnedBuf<double> h_cov;
     PinnedBuf<float> h_T;
+    DevBuf<int> status;                  // raised by launch_chol_whiten when the covariance is not safely SPD
+    PinnedBuf<int> h_status;
     DeviceEigh eig;
     int64_t d = 0, dout = 0;
     void ensure(int64_t d_, int64_t dout_) {
+        if (!status.p) { status.alloc(1); h_status.resize(1); }
         if (d == d_ && dout == dout_) return;
         d = d_; dout = dout_;
         sums.alloc((size_t)d); cov.alloc((size_t)d * d); mean32.alloc((size_t)d); T.alloc((size_t)d * dout);
         h_cov.resize((size_t)d * d); h_T.resize((size_t)d * dout);
+    }
+    void clear_status(cudaStream_t st) { CUDA_TRY(cudaMemsetAsync(status.p, 0, sizeof(int), st)); }
+    // true when no Cholesky step of the loop raised the flag; synchronises `st`
+    bool status_ok(cudaStream_t st) {
+        CUDA_TRY(cudaMemcpyAsync(h_status.data(), status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return h_status.data()[0] == 0;
     }
 };
 
@@ -382,8 +404,10 @@ struct Phase {
 };
 enum { PH_H2D = 0, PH_INIT, PH_SPMM, PH_STATS, PH_EIGH, PH_APPLY, PH_RMSE, PH_D2H };
 
+// `cholesky`: use T = L^-T (chol_whiten.cu) instead of the PCA transform -- only for iterates that are never handed
+// to the caller (see embed_reference_order); dout must equal d then.
 void whiten_device(const float *Y, int64_t n, int64_t d, int64_t dout, float *Z, WhitenState &ws, cudaStream_t st,
-                   Phase &ph) {
+                   Phase &ph, bool cholesky = false) {
     ws.ensure(d, dout);
     ph.begin();
     AbsmaxPartials mx;
@@ -394,7 +418,9 @@ void whiten_device(const float *Y, int64_t n, int64_t d, int64_t dout, float *Z,
     launch_f64_to_f32(ws.sums.p, ws.mean32.p, d, st);                    // mean.astype(float32)
     ph.end(PH_STATS);
     ph.begin();
-    if (current_eigh().fn) {            // host eigensolver installed by the binding (e.g. numpy's LAPACK): one round trip
+    if (cholesky) {
+        launch_chol_whiten(ws.cov.p, d, ws.T.p, ws.status.p, st);
+    } else if (current_eigh().fn) {     // host eigensolver installed by the binding (e.g. numpy's LAPACK): one round trip
         CUDA_TRY(cudaMemcpyAsync(ws.h_cov.data(), ws.cov.p, sizeof(double) * d * d, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         transform_from_cov(ws.h_cov.data(), d, dout, ws.h_T.data());
@@ -419,19 +445,27 @@ struct Persistent {
     }
     void release() {
         for (auto &b : buf) b.free();
-        ws.sums.free(); ws.cov.free(); ws.mean32.free(); ws.T.free();
+        ws.sums.free(); ws.cov.free(); ws.mean32.free(); ws.T.free(); ws.status.free();
         ws.eig.evec.free(); ws.eig.eval.free(); ws.eig.work.free(); ws.eig.info.free();
-        ws.h_cov.release(); ws.h_T.release();
+        ws.h_cov.release(); ws.h_T.release(); ws.h_status.release();
         ws.d = ws.dout = 0; ws.eig.d = 0;
     }
 };
-Persistent &persistent() {
-    static thread_local Persistent p;
-    return p;
+struct SecondStream;
+struct PerDevice {                       // everything a host thread caches on ONE device
+    Persistent ps;
+    std::shared_ptr<SecondStream> side;  // side stream + events of the pipelined loop
+    DeviceEigh eig_misc;                 // cleora_dev_whiten_transform
+};
+PerDevice &per_device() {
+    static thread_local std::map<int, PerDevice> state;
+    return state[current_device()];
 }
+Persistent &persistent() { return per_device().ps; }
 
 // ---- options -------------------------------------------------------------------------------------------------
 std::atomic<int> g_opt_pipeline{1};
+std::atomic<int> g_opt_chol{1};          // Cholesky whitening for iterates that stay inside the loop
 
 // mean / covariance of Y (device) into ws.sums (mean, f64), ws.mean32, ws.cov (scaled by 1/(n-1))
 void stats_device(const float *Y, int64_t n, int64_t d, WhitenState &ws, cudaStream_t st) {
@@ -444,10 +478,12 @@ void stats_device(const float *Y, int64_t n, int64_t d, WhitenState &ws, cudaStr
 }
 
 const float *row_scale_of(DeviceGraph &dg, int markov) {
+    const float *val = values_of(dg, markov);
+    std::lock_guard<std::mutex> lock(dg.lazy_mu);
     float *&slot = markov == CLEORA_MARKOV_LEFT ? dg.rsum_left : dg.rsum_sym;
     if (!slot) {
         CUDA_TRY(cudaMalloc((void **)&slot, sizeof(float) * (size_t)std::max<int64_t>(dg.n_rows, 1)));
-        launch_row_value_sums(dg.rowptr, values_of(dg, markov), dg.n_rows, slot, nullptr);
+        launch_row_value_sums(dg.rowptr, val, dg.n_rows, slot, nullptr);
     }
     return slot;
 }
@@ -484,21 +520,40 @@ bool pipeline_eligible(int64_t n, int64_t d, int64_t iters, int normalization, i
            whiten_apply_tc_supported(d, d);
 }
 
-void embed_pipelined(DeviceGraph &dg, const float *val, int markov, float *cur, float *y, float *w, float *y2, int64_t n,
-                     int64_t d, int64_t iters, WhitenState &ws, Phase &ph, float **result) {
+bool chol_eligible(int64_t d, int normalization) {
+    // row L1 norms are not invariant under an orthogonal change of basis, so only l2 / none keep the loop equivariant
+    return g_opt_chol.load() && chol_whiten_supported(d) &&
+           (normalization == CLEORA_NORM_L2_NUMPY || normalization == CLEORA_NORM_NONE);
+}
+
+// T (device, f32 d x d) from ws.cov through the eigensolver (host callback or cuSOLVER), enqueued on / synchronising `st`.
+void pca_transform(WhitenState &ws, int64_t d, cudaStream_t st) {
+    if (current_eigh().fn) {
+        CUDA_TRY(cudaMemcpyAsync(ws.h_cov.data(), ws.cov.p, sizeof(double) * d * d, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        transform_from_cov(ws.h_cov.data(), d, d, ws.h_T.data());
+        CUDA_TRY(cudaMemcpyAsync(ws.T.p, ws.h_T.data(), sizeof(float) * d * d, cudaMemcpyHostToDevice, st));
+    } else {
+        ws.eig.transform(ws.cov.p, d, d, ws.T.p, st);
+    }
+}
+
+// One attempt of the pipelined loop.  inner_chol: iterations 1 .. T-1 whiten with the Cholesky factor (one-SM kernel
+// on the side stream, no host involvement); otherwise with the eigensolver as in round 1.  Returns false when a
+// Cholesky step flagged its covariance (the caller repeats the loop with the eigensolver; `cur` is not written
+// before the flag has been read).
+bool embed_pipelined_once(DeviceGraph &dg, const float *val, const float *rowscale, float *cur, float *y, float *w,
+                          float *y2, int64_t n, int64_t d, int64_t iters, WhitenState &ws, SecondStream &B, Phase &ph,
+                          bool inner_chol) {
     cudaStream_t A = nullptr;
-    static thread_local std::unique_ptr<SecondStream> side;
-    if (!side) side.reset(new SecondStream());
-    SecondStream &B = *side;
-    ws.ensure(d, d);
-    const float *rowscale = row_scale_of(dg, markov);
+    if (inner_chol) ws.clear_status(A);
     ph.begin();
     launch_spmm(dg, val, cur, d, y, nullptr, 1.f, 0.f, CLEORA_NORM_L2_NUMPY, A);
     ph.end(PH_SPMM);
     ph.begin();
     stats_device(y, n, d, ws, A);
     ph.end(PH_STATS);
-    const bool host_eigh = current_eigh().fn != nullptr;       // e.g. numpy's LAPACK: runs on the CPU while the GPU does the SpMM
+    const bool host_eigh = !inner_chol && current_eigh().fn != nullptr;   // e.g. numpy's LAPACK, on the CPU beside the SpMM
     for (int64_t it = 1; it < iters; ++it) {
         CUDA_TRY(cudaEventRecord(B.stats_done, A));
         CUDA_TRY(cudaStreamWaitEvent(B.s, B.stats_done, 0));
@@ -515,7 +570,8 @@ void embed_pipelined(DeviceGraph &dg, const float *val, int markov, float *cur, 
             CUDA_TRY(cudaEventRecord(B.t_ready, B.s));
         } else {
             ph.begin_on(B.s);
-            ws.eig.transform(ws.cov.p, d, d, ws.T.p, B.s);               // eigensolve || SpMM
+            if (inner_chol) launch_chol_whiten(ws.cov.p, d, ws.T.p, ws.status.p, B.s);   // T = L^-T || SpMM
+            else ws.eig.transform(ws.cov.p, d, d, ws.T.p, B.s);                          // eigensolve || SpMM
             ph.end_on(PH_EIGH, B.s);
             CUDA_TRY(cudaEventRecord(B.t_ready, B.s));
             ph.begin();
@@ -531,21 +587,27 @@ void embed_pipelined(DeviceGraph &dg, const float *val, int markov, float *cur, 
         ph.end(PH_STATS);
         std::swap(y, y2);
     }
+    if (inner_chol && !ws.status_ok(A)) return false;
     ph.begin();
-    if (host_eigh) {
-        CUDA_TRY(cudaMemcpyAsync(ws.h_cov.data(), ws.cov.p, sizeof(double) * d * d, cudaMemcpyDeviceToHost, A));
-        CUDA_TRY(cudaStreamSynchronize(A));
-        transform_from_cov(ws.h_cov.data(), d, d, ws.h_T.data());
-        CUDA_TRY(cudaMemcpyAsync(ws.T.p, ws.h_T.data(), sizeof(float) * d * d, cudaMemcpyHostToDevice, A));
-    } else {
-        ws.eig.transform(ws.cov.p, d, d, ws.T.p, A);
-    }
+    pca_transform(ws, d, A);                                               // the iterate that leaves the loop: PCA
     ph.end(PH_EIGH);
     ph.begin();
     launch_whiten_apply(y, n, d, ws.mean32.p, ws.T.p, d, cur, A);          // X_T = (Y - 1 mu^T) T
     ph.end(PH_APPLY);
     CUDA_TRY(cudaStreamSynchronize(A));
     CUDA_TRY(cudaStreamSynchronize(B.s));
+    return true;
+}
+
+void embed_pipelined(DeviceGraph &dg, const float *val, int markov, float *cur, float *y, float *w, float *y2, int64_t n,
+                     int64_t d, int64_t iters, WhitenState &ws, Phase &ph, float **result) {
+    PerDevice &pd = per_device();
+    if (!pd.side) pd.side = std::make_shared<SecondStream>();
+    ws.ensure(d, d);
+    const float *rowscale = row_scale_of(dg, markov);
+    const bool chol = chol_eligible(d, CLEORA_NORM_L2_NUMPY);
+    if (!embed_pipelined_once(dg, val, rowscale, cur, y, w, y2, n, d, iters, ws, *pd.side, ph, chol))
+        embed_pipelined_once(dg, val, rowscale, cur, y, w, y2, n, d, iters, ws, *pd.side, ph, false);
     *result = cur;
 }
 
@@ -575,8 +637,15 @@ extern "C" int cleora_set_option(const char *key, int64_t value) {
     return guarded([&] {
         const std::string k = key ? key : "";
         if (k == "pipeline_whiten") g_opt_pipeline.store(value != 0);
+        else if (k == "chol_whiten") g_opt_chol.store(value != 0);
         else value_error("unknown option '" + k + "'");
     });
+}
+extern "C" int64_t cleora_get_option(const char *key) {
+    const std::string k = key ? key : "";
+    if (k == "pipeline_whiten") return g_opt_pipeline.load();
+    if (k == "chol_whiten") return g_opt_chol.load();
+    return -1;
 }
 extern "C" int cleora_host_alloc(size_t nbytes, void **out) {
     return guarded([&] { require_device(); CUDA_TRY(cudaMallocHost(out, nbytes ? nbytes : 1)); });
@@ -590,9 +659,7 @@ extern "C" int64_t cleora_dev_workspace_bytes(void) {
 extern "C" int cleora_release_workspace(void) {
     return guarded([&] {
         persistent().release();
-        Workspace &w = workspace();
-        w.colsum_partials.release(); w.gram_partials.release(); w.sqdiff_partials.release(); w.misc.release();
-        w.spmm_partials.release(); w.absmax_partials.release();
+        workspace().release();
     });
 }
 extern "C" int64_t cleora_kernel_launch_count(void) { return g_launches.load(); }
@@ -653,7 +720,8 @@ extern "C" int cleora_graph_from_csr(const int64_t *rowptr, const uint32_t *col,
 }
 extern "C" void cleora_graph_destroy(cleora_graph_t *g) {
     if (!g) return;
-    free_device_graph(g->dev);
+    for (DeviceGraph *dg : g->devs) free_device_graph(dg);
+    g->devs.clear();
     if (g->host_pinned) {
         for (const void *p : {(const void *)g->rowptr.data(), (const void *)g->col.data(), (const void *)g->left.data(),
                               (const void *)g->sym.data()})
@@ -662,7 +730,11 @@ extern "C" void cleora_graph_destroy(cleora_graph_t *g) {
     delete static_cast<Graph *>(g);
 }
 extern "C" int cleora_graph_release_device(cleora_graph_t *g) {
-    return guarded([&] { free_device_graph(g->dev); g->dev = nullptr; });
+    return guarded([&] {
+        std::lock_guard<std::recursive_mutex> lock(g->mu);
+        for (DeviceGraph *dg : g->devs) free_device_graph(dg);
+        g->devs.clear();
+    });
 }
 extern "C" int64_t cleora_graph_num_entities(const cleora_graph_t *g) { return g->n_rows; }
 extern "C" int64_t cleora_graph_num_cols(const cleora_graph_t *g) { return g->n_cols; }
@@ -706,6 +778,7 @@ extern "C" int cleora_graph_copy_entity_ids(const cleora_graph_t *g, char *buf, 
 extern "C" int cleora_graph_set_entity_ids(cleora_graph_t *g, const char *buf, const int64_t *offsets, int64_t n) {
     return guarded([&] {
         if (n != g->n_rows) value_error("entity_ids must keep its length (" + std::to_string(g->n_rows) + ")");
+        std::lock_guard<std::recursive_mutex> lock0(g->mu);
         g->ids.resize((size_t)n);
         g->hash.resize((size_t)n);
         for (int64_t i = 0; i < n; ++i) {
@@ -713,10 +786,10 @@ extern "C" int cleora_graph_set_entity_ids(cleora_graph_t *g, const char *buf, c
             g->hash[(size_t)i] = xxh64(buf + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), 0);
         }
         g->id_index.clear();
-        if (g->dev && g->dev->hash) {
-            CUDA_TRY(cudaSetDevice(g->dev->device));
-            CUDA_TRY(cudaMemcpy(g->dev->hash, g->hash.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice));
-        }
+        std::lock_guard<std::recursive_mutex> lock(g->mu);
+        for (DeviceGraph *dg : g->devs)
+            if (dg->hash)                   // (cudaMemcpy with a device pointer needs no cudaSetDevice under UVA)
+                CUDA_TRY(cudaMemcpy(dg->hash, g->hash.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice));
     });
 }
 extern "C" int cleora_graph_set_descriptor(cleora_graph_t *g, int col_a_id, const char *col_a_name, int col_b_id,
@@ -738,6 +811,7 @@ extern "C" const char *cleora_graph_col_name(const cleora_graph_t *g, int which)
 extern "C" int cleora_graph_col_id(const cleora_graph_t *g, int which) { return which ? g->desc.col_b_id : g->desc.col_a_id; }
 extern "C" int64_t cleora_graph_find_entity(const cleora_graph_t *cg, const char *id, int64_t id_len) {
     Graph *g = const_cast<cleora_graph_t *>(cg);
+    std::lock_guard<std::recursive_mutex> lock(g->mu);      // the index is built lazily; lookups may come from several threads
     if (g->id_index.empty() && !g->ids.empty())
         for (size_t i = 0; i < g->ids.size(); ++i) g->id_index.emplace(g->ids[i], (int64_t)i);   // first wins
     auto it = g->id_index.find(std::string(id, (size_t)id_len));
@@ -854,9 +928,14 @@ extern "C" int cleora_dev_whiten_transform(const double *cov, int64_t d, int64_t
             CUDA_TRY(cudaMemcpyAsync(T, hT.data(), sizeof(float) * d * dout, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaStreamSynchronize(st));
         } else {
-            static thread_local DeviceEigh eig;
-            eig.transform(cov, d, dout, T, st);
+            per_device().eig_misc.transform(cov, d, dout, T, st);
         }
+    });
+}
+extern "C" int cleora_dev_chol_whiten(const double *cov, int64_t d, float *T, int *status, void *stream) {
+    return guarded([&] {
+        if (!chol_whiten_supported(d)) value_error("Cholesky whitening needs 1 <= d <= 512");
+        launch_chol_whiten(cov, d, T, status, (cudaStream_t)stream);
     });
 }
 extern "C" int cleora_whiten_transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T) {
@@ -988,16 +1067,19 @@ extern "C" int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64
         Persistent &ps = persistent();
         DevBuf<double> dsum(1);
         float *cur = ps.get(0, cnt), *y = ps.get(1, cnt), *w = (conv && do_whiten) ? ps.get(2, cnt) : nullptr;
-        if (x0) {
-            ph.begin();
-            CUDA_TRY(cudaMemcpyAsync(cur, x0, cnt * sizeof(float), cudaMemcpyDefault, nullptr));   // host or device
-            ph.end(PH_H2D);
-        } else {
-            if (!dg.hash && n) value_error("graph has no entity hashes");
-            ph.begin();
-            launch_init(dg.hash, n, d, seed, cur, nullptr);
-            ph.end(PH_INIT);
-        }
+        auto load_x0 = [&] {
+            if (x0) {
+                ph.begin();
+                CUDA_TRY(cudaMemcpyAsync(cur, x0, cnt * sizeof(float), cudaMemcpyDefault, nullptr));   // host or device
+                ph.end(PH_H2D);
+            } else {
+                if (!dg.hash && n) value_error("graph has no entity hashes");
+                ph.begin();
+                launch_init(dg.hash, n, d, seed, cur, nullptr);
+                ph.end(PH_INIT);
+            }
+        };
+        load_x0();
         const bool use_res = residual_weight > 0.0;              // pycleora/__init__.py:114 (no < 1 guard)
         const float alpha = (float)(1.0 - residual_weight), rwf = (float)residual_weight;
         WhitenState &ws = ps.ws;
@@ -1008,31 +1090,48 @@ extern "C" int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64
             embed_pipelined(dg, val, markov, cur, y, ps.get(3, cnt), ps.get(4, cnt), n, d, iters, ws, ph, &result);
             done = iters;
         }
-        for (int64_t it = 0; it < (pipelined ? 0 : iters); ++it) {
-            ph.begin();
-            launch_spmm(dg, val, cur, d, y, use_res ? cur : nullptr, alpha, rwf, normalization, nullptr);
-            ph.end(PH_SPMM);
-            float *fresh;
-            if (do_whiten) {
-                fresh = conv ? w : cur;                          // without rmse the old iterate can be overwritten
-                whiten_device(y, n, d, d, fresh, ws, nullptr, ph);
-            } else {
-                fresh = y;
-            }
-            done = it + 1;
-            bool stop = false;
-            if (conv && it > 0) {                                // _compute_rmse, pycleora/__init__.py:974-976
+        // Reference stage order.  Without the rmse early stop no intermediate iterate is visible to the caller, so
+        // iterations 0 .. T-2 may whiten with the Cholesky factor (chol_whiten.cu: same final iterate, no eigensolve);
+        // with it, every iterate is compared element-wise with its predecessor and keeps the PCA basis.
+        auto reference_order = [&](bool inner_chol) -> bool {
+            if (inner_chol) { ws.ensure(d, d); ws.clear_status(nullptr); }
+            for (int64_t it = 0; it < iters; ++it) {
                 ph.begin();
-                launch_sq_diff_sum(fresh, cur, (int64_t)cnt, true, dsum.p, nullptr);
-                double h = 0.0;
-                CUDA_TRY(cudaMemcpy(&h, dsum.p, sizeof(double), cudaMemcpyDeviceToHost));
-                ph.end(PH_RMSE);
-                stop = std::sqrt(h / (double)cnt) < convergence_threshold;
+                launch_spmm(dg, val, cur, d, y, use_res ? cur : nullptr, alpha, rwf, normalization, nullptr);
+                ph.end(PH_SPMM);
+                float *fresh;
+                if (do_whiten) {
+                    fresh = conv ? w : cur;                      // without rmse the old iterate can be overwritten
+                    const bool last = it + 1 == iters;
+                    if (inner_chol && last && !ws.status_ok(nullptr)) return false;     // before the last overwrite
+                    whiten_device(y, n, d, d, fresh, ws, nullptr, ph, inner_chol && !last);
+                } else {
+                    fresh = y;
+                }
+                done = it + 1;
+                bool stop = false;
+                if (conv && it > 0) {                            // _compute_rmse, pycleora/__init__.py:974-976
+                    ph.begin();
+                    launch_sq_diff_sum(fresh, cur, (int64_t)cnt, true, dsum.p, nullptr);
+                    double h = 0.0;
+                    CUDA_TRY(cudaMemcpy(&h, dsum.p, sizeof(double), cudaMemcpyDeviceToHost));
+                    ph.end(PH_RMSE);
+                    stop = std::sqrt(h / (double)cnt) < convergence_threshold;
+                }
+                if (fresh == w) std::swap(cur, w);
+                else if (fresh == y) std::swap(cur, y);
+                result = cur;
+                if (stop) break;
             }
-            if (fresh == w) std::swap(cur, w);
-            else if (fresh == y) std::swap(cur, y);
-            result = cur;
-            if (stop) break;
+            return true;
+        };
+        if (!pipelined) {
+            const bool inner_chol = do_whiten && !conv && iters >= 2 && chol_eligible(d, normalization);
+            if (!reference_order(inner_chol)) {                  // a covariance was not safely SPD: eigensolver throughout
+                cur = ps.get(0, cnt); y = ps.get(1, cnt);
+                load_x0();
+                reference_order(false);
+            }
         }
         ph.begin();
         CUDA_TRY(cudaMemcpyAsync(out, result, cnt * sizeof(float), cudaMemcpyDefault, nullptr));   // host or device

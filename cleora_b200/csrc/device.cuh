@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdint>
 #include <climits>
+#include <mutex>
 #include <string>
 
 namespace cleora {
@@ -26,6 +27,7 @@ struct DeviceGraph {
     int64_t *long_chunk_ptr = nullptr;     // [n_long + 1] first chunk of each long row
     int32_t *long_chunk_owner = nullptr;   // [n_long_chunks] index into long_rows
     float *rsum_left = nullptr, *rsum_sym = nullptr;   // A*1 per Markov type, built on first pipelined use
+    std::mutex lazy_mu;                    // guards the lazily built members (sym, rsum_*)
 };
 
 // Extra destinations of a row-producing kernel: the same rows are also stored at these base pointers (peer GPUs'
@@ -65,9 +67,14 @@ struct Scratch {
     void release();
 };
 struct Workspace {
-    Scratch colsum_partials, gram_partials, sqdiff_partials, misc, spmm_partials, absmax_partials;
+    Scratch colsum_partials, gram_partials, sqdiff_partials, misc, spmm_partials, absmax_partials, chol;
     size_t bytes() const {
-        return colsum_partials.cap + gram_partials.cap + sqdiff_partials.cap + misc.cap + spmm_partials.cap + absmax_partials.cap;
+        return colsum_partials.cap + gram_partials.cap + sqdiff_partials.cap + misc.cap + spmm_partials.cap +
+               absmax_partials.cap + chol.cap;
+    }
+    void release() {
+        colsum_partials.release(); gram_partials.release(); sqdiff_partials.release(); misc.release();
+        spmm_partials.release(); absmax_partials.release(); chol.release();
     }
 };
 Workspace &workspace();
@@ -97,5 +104,8 @@ void launch_sq_diff_sum(const float *a, const float *b, int64_t n, bool f64_diff
 void launch_build_transform(const double *V, const double *w, int64_t d, int64_t dout, float *T, cudaStream_t st);
 void launch_scale_f64(double *v, int64_t n, double factor, cudaStream_t st);
 void launch_f64_to_f32(const double *in, float *out, int64_t n, cudaStream_t st);
+// Cholesky whitening (chol_whiten.cu): T = L^-T of cov = L L^T as f32; status[0] raised when cov is not safely SPD.
+bool chol_whiten_supported(int64_t d);
+void launch_chol_whiten(const double *cov, int64_t d, float *T, int *status, cudaStream_t st);
 
 }  // namespace cleora

@@ -5,6 +5,7 @@
 #include <vector>
 #include <unordered_map>
 #include <memory>
+#include <mutex>
 
 namespace cleora {
 
@@ -36,7 +37,9 @@ struct Graph {
     std::vector<uint8_t> column_id;       // n_rows
     std::vector<std::string> ids;         // n_rows (may be empty for adopted CSR)
     std::unordered_map<std::string, int64_t> id_index;   // built lazily by find()
-    DeviceGraph *dev = nullptr;           // lazily uploaded copy, owned
+    std::vector<DeviceGraph *> devs;      // lazily uploaded copies, one per device that used the graph; owned
+    std::recursive_mutex mu;              // guards the lazy caches (devs and their lazily built members, id_index):
+                                          // ctypes drops the GIL, so two Python threads may share one graph
     bool host_pinned = false;             // CSR arrays page-locked (cudaHostRegister) for fast (re-)uploads
     int64_t nnz() const { return (int64_t)col.size(); }
 };

@@ -139,6 +139,14 @@ class CudaBackend:
         """cov (device f64, scaled) -> T (device f32) on the current stream (cuSOLVER unless a host eigh is set)."""
         check(self.L.cleora_dev_whiten_transform(cov.data_ptr(), d, d, T.data_ptr(), self.stream()))
 
+    def chol(self, cov, d: int, T, status) -> None:
+        """cov (device f64, scaled) -> T = L^-T (device f32) on the current stream; status (int32[1]) is raised when cov
+        is not safely positive definite (chol_whiten.cu)."""
+        check(self.L.cleora_dev_chol_whiten(cov.data_ptr(), d, T.data_ptr(), status.data_ptr(), self.stream()))
+
+    def chol_enabled(self, d: int) -> bool:
+        return d <= 512 and self.L.cleora_get_option(b"chol_whiten") == 1
+
     def fusable(self, d: int) -> bool:
         return bool(self.L.cleora_whiten_apply_fusable(d, d))
 
@@ -271,6 +279,8 @@ class ShardedEmbedder:
         self.mean32 = be.empty((d,), torch.float32)
         self.T = be.empty((d, d), torch.float32)
         self.scalar = be.empty((1,), torch.float64)
+        self.status = be.empty((1,), torch.int32)               # raised by the Cholesky whitening kernel
+        self.status.zero_()
         self.hash_pad = be.from_numpy(s.hash_padded.view(np.int64)) if s.n_pad else be.empty((1,), torch.int64)
         self.phase_ms = {}
         if s.n_pad:
@@ -302,7 +312,7 @@ class ShardedEmbedder:
 
     def run(self, iters: int, markov: int = 0, norm: int = _lib.NORM_L2_NUMPY, seed: int = 0,
             x0: Optional[np.ndarray] = None, residual_weight: float = 0.0, convergence_threshold: float = 0.0,
-            whiten: bool = True, rust_semantics: bool = False, timers=None) -> int:
+            whiten: bool = True, rust_semantics: bool = False, timers=None, _allow_chol: bool = True) -> int:
         """Leaves the final iterate in self.x_full (padded layout) on every rank; returns iterations done."""
         torch, dist, be, s, d = self.torch, self.dist, self.be, self.shard, self.d
         n = s.n
@@ -320,6 +330,13 @@ class ShardedEmbedder:
         do_whiten = whiten and n > 1
         if conv and self.x_prev is None:
             self.x_prev = be.empty(tuple(self.x_full.shape), torch.float32)
+        # iterates that never leave the loop are whitened with the Cholesky factor, computed redundantly (and
+        # identically: the all-reduced covariance is bit-identical everywhere) on every rank -- no eigensolve, no
+        # broadcast; the last iterate gets the reference's PCA transform (see chol_whiten.cu for the argument)
+        inner_chol = (_allow_chol and do_whiten and not conv and iters >= 2 and hasattr(be, "chol") and be.chol_enabled(d)
+                      and norm in (_lib.NORM_L2_NUMPY, _lib.NORM_NONE))
+        if inner_chol:
+            self.status.zero_()
         done = 0
         for it in range(iters):
             if conv:
@@ -347,9 +364,12 @@ class ShardedEmbedder:
                 if timers:
                     timers.stop(t)
                 t = timers.start("eigh") if timers else None
-                if s.rank == 0:
-                    be.transform(self.cov, d, self.T)
-                dist.broadcast(self.T, src=0, group=self.group)       # one eigensolve, identical T everywhere
+                if inner_chol and it + 1 < iters:
+                    be.chol(self.cov, d, self.T, self.status)
+                else:
+                    if s.rank == 0:
+                        be.transform(self.cov, d, self.T)
+                    dist.broadcast(self.T, src=0, group=self.group)   # one eigensolve, identical T everywhere
                 if timers:
                     timers.stop(t)
                 t = timers.start("apply") if timers else None
@@ -375,7 +395,16 @@ class ShardedEmbedder:
                     rmse = float(np.sqrt(tot / (n * d)))
                 if rmse < convergence_threshold:
                     break
+        if inner_chol and not self._chol_status_ok():
+            return self.run(iters, markov, norm, seed, x0, residual_weight, convergence_threshold, whiten,
+                            rust_semantics, timers, _allow_chol=False)
         return done
+
+    def _chol_status_ok(self) -> bool:
+        """No rank's Cholesky step flagged its covariance (identical inputs, so in practice all or none)."""
+        flag = self.status.clone()
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX, group=self.group)
+        return int(flag.item()) == 0
 
     # ------------------------------------------------------------------------------------------ pipelined variant
     def pipeline_eligible(self, iters, norm, residual_weight, convergence_threshold, whiten) -> bool:
@@ -398,7 +427,7 @@ class ShardedEmbedder:
             timers.stop(t)
 
     def run_pipelined(self, iters: int, markov: int = 0, seed: int = 0, x0: Optional[np.ndarray] = None,
-                      timers=None) -> int:
+                      timers=None, _allow_chol: bool = True) -> int:
         """Same mathematics as run() for the default configuration, with the eigensolve (rank 0, side stream) hidden
         behind the local SpMM via A (Y - 1 mu^T) T = (A Y - (A 1) mu^T) T, and the all-gather of the next iterate
         (own communicator, own stream) hidden behind the covariance pass.  x_full holds the gathered NORMALISED
@@ -413,6 +442,9 @@ class ShardedEmbedder:
             self._pl["markov"] = None
         pl = self._pl
         side, comm, w, rowscale = pl["side"], pl["comm"], pl["w"], pl["rowscale"]
+        inner_chol = _allow_chol and hasattr(be, "chol") and be.chol_enabled(d)
+        if inner_chol:
+            self.status.zero_()
         if pl["markov"] != markov:
             be.row_scale(s, markov, rowscale)
             pl["markov"] = markov
@@ -439,9 +471,15 @@ class ShardedEmbedder:
         for it in range(1, iters):
             side.wait_stream(main)                                   # cov of this iterate is ready
             with be.on(side):
-                if s.rank == 0:
-                    be.transform(self.cov, d, self.T)
-                dist.broadcast(self.T, src=0, group=pl["g_bcast"])
+                t = timers.start("eigh") if timers else None
+                if inner_chol:
+                    be.chol(self.cov, d, self.T, self.status)        # every rank, identical input -> identical T
+                else:
+                    if s.rank == 0:
+                        be.transform(self.cov, d, self.T)
+                    dist.broadcast(self.T, src=0, group=pl["g_bcast"])
+                if timers:
+                    timers.stop(t)
             main.wait_stream(comm)                                   # gathered Y is complete
             t = timers.start("spmm") if timers else None
             be.spmm(s, markov, self.x_full, d, w, None, 1.0, 0.0, _lib.NORM_NONE)      # W = A Y (own rows)
@@ -461,10 +499,13 @@ class ShardedEmbedder:
                 timers.stop(t)
             comm.wait_stream(main)
             with be.on(comm):
+                t = timers.start("gather") if timers else None
                 if push:
                     self._flip(pl["g_gather"])                                         # node-wide barrier, beside the stats
                 else:
                     dist.all_gather_into_tensor(self.x_full, y2, group=pl["g_gather"])  # next Y, beside the stats
+                if timers:
+                    timers.stop(t)
             self._stats(y2, timers)
             if not push:
                 y, y2 = y2, y
@@ -478,6 +519,8 @@ class ShardedEmbedder:
         out_final = self.z if push else y2             # (with the fused gather y aliases the gathered matrix)
         be.apply(y, s.n_local, d, self.mean32, self.T, out_final)
         self._gather(out_final)
+        if inner_chol and not self._chol_status_ok():               # a covariance was not safely SPD: eigensolver throughout
+            return self.run_pipelined(iters, markov, seed, x0, timers, _allow_chol=False)
         return iters
 
     def result(self) -> np.ndarray:

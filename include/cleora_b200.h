@@ -147,10 +147,18 @@ void cleora_set_eigh(cleora_eigh_fn fn, void *user);            /* process-wide 
  * mode 0 = follow the process-wide setting again.  Lets a binding scope an eigensolver to one call. */
 void cleora_set_eigh_thread(int mode, cleora_eigh_fn fn, void *user);
 
-/* Tuning switches.  "pipeline_whiten" (default 1): in cleora_embed's default configuration (whiten, l2, no residual,
- * no early stop, d % 32 == 0, d <= 256) overlap the eigensolve with the next SpMM using
- * A (Y - 1 mu^T) T = (A Y - (A 1) mu^T) T; 0 keeps the reference's stage order exactly. */
+/* Tuning switches.
+ * "pipeline_whiten" (default 1): in cleora_embed's default configuration (whiten, l2, no residual, no early stop,
+ *   tensor-core apply available for d) compute W = A Y while the transform of Y is being built, using
+ *   A (Y - 1 mu^T) T = (A Y - (A 1) mu^T) T; 0 keeps the reference's stage order exactly.
+ * "chol_whiten" (default 1): iterates that never leave the loop (iterations 0 .. T-2 of a call without rmse early
+ *   stop, l2 / none normalisation, d <= 512) are whitened with the Cholesky factor T = L^-T of the covariance instead
+ *   of the PCA transform of pycleora/__init__.py:145-156; the loop body is equivariant under orthogonal
+ *   right-multiplication, so the final iterate (always PCA-whitened) is the reference's.  Falls back to the
+ *   eigensolver for the whole call when a covariance is not safely positive definite (lambda_min near the reference's
+ *   1e-10 clamp).  0 = eigensolver in every iteration. */
 int cleora_set_option(const char *key, int64_t value);
+int64_t cleora_get_option(const char *key);      /* -1 for an unknown key */
 
 /* Pinned host staging memory for callers that want async copies (bench e2e). */
 int cleora_host_alloc(size_t nbytes, void **out);
@@ -210,6 +218,11 @@ int cleora_dev_sq_diff_sum(const float *a, const float *b, int64_t n, int f64_di
  * a transform-building kernel, no host synchronisation -- unless a host eigensolver is installed
  * (cleora_set_eigh), in which case the call makes one synchronous round trip. */
 int cleora_dev_whiten_transform(const double *cov, int64_t d, int64_t dout, float *T, void *stream);
+/* Cholesky whitening on `stream` (one-SM f64 kernel, no library call, no host synchronisation): cov (f64 [d, d], device,
+ * already divided by n-1) = L L^T  ->  T = L^-T as f32 [d, d] (upper triangular, T^T cov T = I).  status (int[1],
+ * device) is set to 1 -- never cleared -- when a pivot is not positive or trace(cov^-1) > 1e8, i.e. when the PCA
+ * transform with its 1e-10 clamp (pycleora/__init__.py:155) might not be a whitening of the same matrix.  d <= 512. */
+int cleora_dev_chol_whiten(const double *cov, int64_t d, float *T, int *status, void *stream);
 /* Host step of the whitening: cov (f64, already divided by n-1) -> T (f32 [d, dout]) via the installed eigh. */
 int cleora_whiten_transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T);
 /* The calling thread keeps its iterate buffers, whitening scratch and cuSOLVER handle between calls (re-creating
