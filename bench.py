@@ -6,7 +6,9 @@
   python bench.py --impl reference --gpus 1 --steps 2 --warmup 1  # the reference's CPU path (restated: oracle/)
 
 A "step" is one full pass of the hot path over the workload: init -> 40 x (SpMM -> L2 -> whiten).  Default
-workload = BASELINE.json configs[1]: Erdos-Renyi 1M nodes / 20M edges, d=256, iters=40.
+workload = BASELINE.json configs[2], the configuration it lists for 1/2/4/8 GPUs: ogbn-products-shaped Chung-Lu graph,
+2.45M nodes / 61.9M edges, d=256, iters=40 (it fits one GPU).  `--workload er-1m-20m-d256` is
+configs[1] (C2), the round-1 default.
 `value`  : E * iters / t with graph and state resident in HBM, timed with CUDA events on the library's stream.
 `e2e`    : the same metric through the public host-buffer API (cleora_b200.embed on host arrays): CSR upload
            and result download inside the timed region.
@@ -132,8 +134,8 @@ def oracle_graph_from(g):
 def run_reference(args, w, name):
     """--impl reference: the reference's own CPU implementation of the path.  The Rust crate cannot be built
     here (no cargo/rustc), so this is the oracle port: C/OpenMP restatement of src/embedding.rs + the
-    reference's numpy whitening, all host threads.  One step = `sample_iters` iterations of the full workload."""
-    import cleora_b200 as cb
+    reference's numpy whitening, all host threads.  One step = `sample_iters` iterations of the full workload.
+    Nothing of the product is loaded in this arm: the CSR comes from the oracle's own integer ingest."""
     import oracle
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -141,9 +143,7 @@ def run_reference(args, w, name):
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     u, v = gen_pairs(w)
-    g = cb.SparseMatrix.from_edge_arrays(u, v)          # host-only: CSR construction (no GPU work)
-    og = oracle_graph_from(g)
-    oracle.lib()
+    og = oracle.graph_from_pairs(u, v)                  # host-only CSR construction, outside the timed region
     sample_iters = args.cpu_iters
     for _ in range(min(args.warmup, 1)):
         cpu_loop(og, w["d"], 1, args.whiten, cores)
@@ -155,14 +155,76 @@ def run_reference(args, w, name):
         "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "nodes": g.num_entities, "edges": int(len(u)), "nnz": g.num_edges, "d": w["d"],
+        "config": {"workload": name, "nodes": og.n, "edges": int(len(u)), "nnz": og.nnz, "d": w["d"],
                    "iters": args.iters, "whiten": bool(args.whiten)},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port",
                          "sample": f"{sample_iters} of {args.iters} iterations of the full workload per step "
                                    "(restated Rust/rayon SpMM+L2 in C/OpenMP + the reference's numpy whitening)"},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "product_library_loaded": any("libcleora_b200" in ln for ln in open("/proc/self/maps")),
     }
     print(json.dumps(line), flush=True)
+
+
+def torch_baseline(g, d, sample_iters):
+    """Second stated baseline: the reference's OWN GPU path, `propagate_gpu`
+    (pycleora/__init__.py:684-739: coalesced COO `torch.sparse.mm` (cuSPARSE), row L2 norm, and
+    `_whiten_embeddings_torch`, :979-997: f32 mean / covariance GEMM, `torch.linalg.eigh`, rsqrt-scaled transform
+    GEMM), restated here stage for stage with the same torch calls, on the same GPU, same graph.  Returns seconds per
+    iteration (CUDA events; one warm-up iteration)."""
+    import torch
+    rows, cols, vals, n, _ = g.to_sparse_csr("left")
+    idx = torch.stack([torch.from_numpy(rows.astype(np.int64)), torch.from_numpy(cols.astype(np.int64))])
+    adj = torch.sparse_coo_tensor(idx, torch.from_numpy(vals), size=(n, n)).to("cuda").coalesce()
+    del idx
+    emb = torch.rand((n, d), device="cuda", dtype=torch.float32) * 2 - 1
+
+    def one(emb):
+        emb = torch.sparse.mm(adj, emb)
+        emb = emb / torch.norm(emb, dim=1, keepdim=True).clamp(min=1e-10)
+        mean = emb.mean(dim=0, keepdim=True)
+        centered = emb - mean
+        cov = centered.transpose(0, 1).matmul(centered) / max(n - 1, 1)
+        w_, v_ = torch.linalg.eigh(cov)
+        order = torch.argsort(w_, descending=True)
+        transform = v_[:, order] * torch.rsqrt(torch.clamp(w_[order], min=1e-10)).unsqueeze(0)
+        return centered.matmul(transform)
+
+    emb = one(emb)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(sample_iters):
+        emb = one(emb)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / sample_iters
+
+
+def parity_probe(d, iters):
+    """Small in-process parity check of the configuration being timed (not in the timed region): ER 20k nodes /
+    200k pairs, the workload's d and iteration count, default options, against the CPU oracle's reference-order
+    loop (pycleora/__init__.py:109-125,963-971).  Bars as in tests/test_gpu_parity.py."""
+    import cleora_b200 as cb
+    import oracle
+    from tests.helpers import gram_err, procrustes_err
+    rs = np.random.default_rng(7)
+    n, e = 20000, 200000
+    u, v = rs.integers(0, n, e), rs.integers(0, n, e)
+    k = u != v
+    g = cb.SparseMatrix.from_edge_arrays(u[k], v[k])
+    og = oracle.graph_from_pairs(u[k], v[k])
+    t0 = time.perf_counter()
+    got = cb.embed(g, d, iters)
+    ref = oracle.embed(og, d, iters)
+    pe, ge = procrustes_err(got, ref), gram_err(got, ref)
+    fast = cb.embed(g, d, iters, whiten=False)
+    fref = oracle.embed(og, d, iters, whiten=False)
+    fe = float(np.max(np.abs(fast.astype(np.float64) - fref)) / np.max(np.abs(fref)))
+    return {"graph": f"ER {n} nodes / {int(k.sum())} pairs, d={d}, {iters} iterations, default options",
+            "whiten_procrustes_err": pe, "whiten_gram_err": ge, "whiten_ok": bool(pe <= 1e-4 and ge <= 1e-5),
+            "nowhiten_max_err_of_scale": fe, "nowhiten_ok": bool(fe <= 1e-5),
+            "seconds": round(time.perf_counter() - t0, 2)}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -224,24 +286,23 @@ def run_ours(args, w, name):
     t_wall = time.perf_counter() - t_wall
     launches = L.cleora_kernel_launch_count() - launches0
     clk = clocks.stop()
-    eigh_ctx.__exit__(None, None, None)
     ms_step = ev0.elapsed_time(ev1) / args.steps
     value = E * iters / (ms_step * 1e-3)
 
-    # ---- e2e: public host API, host buffers, CSR upload + result download inside the timed region
+    # ---- e2e: public host API, host buffers; every step copies the CSR host -> device again (same device buffers,
+    # pinned host arrays) and the result device -> pinned host memory inside the timed region.  X0 is produced on the
+    # device by the init kernel from the uploaded entity hashes (the reference also initialises inside embed()).
     pinned = cb.pinned_empty((n, d), np.float32)
     e2e_times = []
     for i in range(1 + args.e2e_steps):
-        _lib.check(L.cleora_graph_release_device(g._handle()))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        if args.whiten:
-            g.embed_device(d, iters, "left", norm, 0, None, 0.0, 0.0, True, out=pinned)
-        else:
-            g.embed_device(d, iters, "left", norm, 0, None, 0.0, 0.0, False, out=pinned)
+        _lib.check(L.cleora_graph_refresh_device(g._handle(), None))
+        g.embed_device(d, iters, "left", norm, 0, None, 0.0, 0.0, bool(args.whiten), out=pinned)
         torch.cuda.synchronize()
         if i > 0:
             e2e_times.append(time.perf_counter() - t0)
+    eigh_ctx.__exit__(None, None, None)
     e2e_t = sum(e2e_times) / len(e2e_times)
     h2d = 8 * (n + 1) + nnz * (4 + 4) + 8 * n     # rowptr + col + left values + hashes (sym values only on first symmetric use)
     d2h = 4 * n * d
@@ -256,6 +317,25 @@ def run_ours(args, w, name):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(name)
 
+    # ---- parity of the timed configuration (small graph, against the CPU oracle; outside the timed region)
+    parity = None
+    if not args.no_parity:
+        parity = parity_probe(d, iters)
+
+    # ---- second stated baseline: the reference's own torch GPU path on this GPU (bounded sample)
+    tbase = None
+    if args.torch_iters > 0:
+        try:
+            L.cleora_release_workspace()
+            torch.cuda.empty_cache()
+            tt = torch_baseline(g, d, args.torch_iters)
+            tbase = {"value": E / tt, "unit": "edges/s", "ms_per_iter": 1e3 * tt,
+                     "what": "reference's propagate_gpu restated with the same torch calls (pycleora/__init__.py:684-739,"
+                             "979-997): coalesced COO torch.sparse.mm + row norm + f32 covariance GEMM + torch.linalg.eigh "
+                             "+ transform GEMM", "sample": f"{args.torch_iters} iterations after 1 warm-up"}
+        except Exception as ex:  # noqa: BLE001 - a baseline must not break the bench line
+            tbase = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
     # ---- CPU baseline beside it: bounded sample of the same workload on the host cores
     cpu = None
     if not args.no_cpu_baseline:
@@ -269,17 +349,23 @@ def run_ours(args, w, name):
                "sample": f"{args.cpu_iters} of {iters} iterations of the full workload, restated Rust/rayon SpMM+L2 "
                          "(C/OpenMP, oracle/) + the reference's numpy whitening"}
 
+    chol = bool(L.cleora_get_option(b"chol_whiten")) and bool(args.whiten)
     line = {
         "metric": "edges/sec through the 40-iteration embed() loop", "value": value, "unit": "edges/s",
         "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "nodes": n, "edges": E, "nnz": nnz, "d": d, "iters": iters,
-                   "whiten": bool(args.whiten), "eigh": _lib.eigh_mode() + (" -> numpy LAPACK on the host, overlapped with the SpMM" if host_eigh else " -> cuSOLVER"),
-                   "pipeline_whiten": os.environ.get("CLEORA_B200_PIPELINE", "1") != "0",
-                   "l2_flush": "inputs (X 1.0 GB + CSR 0.33 GB per iteration) exceed the 126 MB L2"},
+                   "whiten": bool(args.whiten),
+                   "inner_whitening": ("Cholesky factor on the device (iterations 0..T-2), PCA eigh on the last" if chol
+                                       else "PCA eigh every iteration"),
+                   "eigh": "numpy LAPACK on the host" if host_eigh else "cuSOLVER Dsyevd",
+                   "pipeline_whiten": bool(L.cleora_get_option(b"pipeline_whiten")),
+                   "l2_flush": "inputs (X + CSR per iteration) exceed the 126 MB L2"},
         "nnz_per_s": nnz * iters / (ms_step * 1e-3),
         "e2e": {"value": E * iters / e2e_t, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_t},
+                "ms_per_step": 1e3 * e2e_t, "samples": len(e2e_times), "ms_min": 1e3 * min(e2e_times),
+                "note": "cleora_b200 host API on host buffers: CSR re-copied host->device and result copied to pinned "
+                        "host memory every step; X0 comes from the init kernel (entity hashes are part of the upload)"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel (K1: SpMM + fused L2)", "achieved": achieved,
@@ -288,6 +374,8 @@ def run_ours(args, w, name):
         "phase_ms_per_iter": {k: timings[i] / (iters * args.steps) for i, k in
                               enumerate(["h2d", "init", "spmm", "stats", "eigh", "apply", "rmse", "d2h"])},
         "wall_ms_per_step": 1e3 * t_wall / args.steps,
+        "parity": parity,
+        "torch_baseline": tbase,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -308,12 +396,14 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="er-1m-20m-d256", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="products-2.4m-62m-d256", choices=sorted(WORKLOADS))
     ap.add_argument("--iters", type=int, default=40)
     ap.add_argument("--whiten", type=int, default=1)
-    ap.add_argument("--cpu-iters", type=int, default=2, help="iterations per CPU sample (bounded baseline)")
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--cpu-iters", type=int, default=1, help="iterations per CPU sample (bounded baseline)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--torch-iters", type=int, default=3, help="iterations of the reference's torch GPU path (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

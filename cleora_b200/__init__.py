@@ -17,7 +17,7 @@ from ._lib import check, ptr
 from .pycleora import SparseMatrix
 
 __all__ = ["SparseMatrix", "embed", "whiten_embeddings", "embed_using_baseline_cleora", "embed_multiscale",
-           "embed_with_node_features", "embed_inductive", "update_graph", "pinned_empty", "set_option",
+           "embed_with_node_features", "embed_inductive", "update_graph", "pinned_empty", "set_option", "synth_pairs",
            "release_workspace", "DEFAULT_FEATURE_DIM", "DEFAULT_NUM_ITERATIONS"]
 
 DEFAULT_FEATURE_DIM = 256          # pycleora/__init__.py:12
@@ -49,6 +49,21 @@ def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     weakref.finalize(buf, _lib.lib().cleora_host_free, p)
     return arr
+
+
+def synth_pairs(kind: str, n_nodes: int, n_pairs: int, seed: int = 0, alpha: float = 0.5):
+    """Synthetic edge list generated on the current GPU (counter-based RNG, include/cleora_b200.h:
+    cleora_dev_synth_pairs): ``kind`` "er" (uniform endpoints) or "chunglu" (endpoint weights (i+10)^-alpha).
+    Returns two torch int32 CUDA tensors holding the unsigned 32-bit ids; u != v."""
+    import torch
+    kinds = {"er": 0, "chunglu": 1}
+    if kind not in kinds:
+        raise ValueError(f"unknown synthetic graph kind '{kind}'")
+    u = torch.empty(int(n_pairs), dtype=torch.int32, device="cuda")
+    v = torch.empty(int(n_pairs), dtype=torch.int32, device="cuda")
+    check(_lib.lib().cleora_dev_synth_pairs(kinds[kind], int(n_nodes), int(n_pairs), int(seed), float(alpha),
+                                            u.data_ptr(), v.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return u, v
 
 
 def _validate_propagation(propagation: str) -> None:

@@ -36,10 +36,17 @@ PROTOTYPES = {
     "cleora_graph_from_lines": (C.c_int, [C.c_char_p, c_i64p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "cleora_graph_from_files": (C.c_int, [C.POINTER(C.c_char_p), C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "cleora_graph_from_pairs": (C.c_int, [c_u32p, c_u32p, C.c_int64, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "cleora_dev_graph_from_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p, C.POINTER(C.c_void_p), c_i64p]),
+    "cleora_dev_synth_pairs": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
+    "cleora_dev_graph_hashes": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), c_i64p]),
+    "cleora_graph_num_entities_global": (C.c_int64, [C.c_void_p]),
     "cleora_graph_from_csr": (C.c_int, [c_i64p, c_u32p, c_f32p, c_f32p, c_f32p, c_u64p, C.c_int64, C.c_int64,
                                         C.c_int64, C.POINTER(C.c_void_p)]),
     "cleora_graph_destroy": (None, [C.c_void_p]),
     "cleora_graph_release_device": (C.c_int, [C.c_void_p]),
+    "cleora_graph_refresh_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cleora_graph_num_entities": (C.c_int64, [C.c_void_p]),
     "cleora_graph_num_cols": (C.c_int64, [C.c_void_p]),
     "cleora_graph_num_edges": (C.c_int64, [C.c_void_p]),

@@ -118,8 +118,41 @@ void free_device_graph(DeviceGraph *dg) {
     if (!dg) return;
     cudaFree(dg->rowptr); cudaFree(dg->col); cudaFree(dg->left); cudaFree(dg->sym); cudaFree(dg->hash);
     cudaFree(dg->long_rows); cudaFree(dg->long_chunk_ptr); cudaFree(dg->long_chunk_owner);
-    cudaFree(dg->rsum_left); cudaFree(dg->rsum_sym);
+    cudaFree(dg->rsum_left); cudaFree(dg->rsum_sym); cudaFree(dg->row_sum_all); cudaFree(dg->orig_ids);
     delete dg;
+}
+
+// Long-row schedule (degree skew): rows above the threshold are processed chunk-wise by separate warps.
+// The default threshold is deliberately high: a chunked f32 sum differs from the reference's sequential sum by
+// ~sqrt(deg) ulp (measured 1e-5 relative at 30k edges, and that feeds back through 40 iterations on star-like graphs),
+// so splitting is reserved for hubs whose sequential walk would dominate the launch.
+void attach_long_row_schedule(DeviceGraph &d, const std::vector<int64_t> &rowptr) {
+    DeviceGraph *dg = &d;
+    const int64_t n_rows = (int64_t)rowptr.size() - 1;
+    const int64_t threshold = env_int64("CLEORA_B200_LONG_ROW", 65536), chunk = env_int64("CLEORA_B200_LONG_CHUNK", 4096);
+    std::vector<int64_t> rows, cptr{0};
+    std::vector<int32_t> owner;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t deg = rowptr[(size_t)r + 1] - rowptr[(size_t)r];
+        if (deg > threshold) {
+            const int64_t nc = (deg + chunk - 1) / chunk;
+            for (int64_t c = 0; c < nc; ++c) owner.push_back((int32_t)rows.size());
+            rows.push_back(r);
+            cptr.push_back(cptr.back() + nc);
+        }
+    }
+    dg->long_threshold = threshold;
+    dg->long_chunk_edges = chunk;
+    dg->n_long = (int64_t)rows.size();
+    dg->n_long_chunks = (int64_t)owner.size();
+    if (!rows.empty()) {
+        CUDA_TRY(cudaMalloc((void **)&dg->long_rows, rows.size() * sizeof(int64_t)));
+        CUDA_TRY(cudaMemcpy(dg->long_rows, rows.data(), rows.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc((void **)&dg->long_chunk_ptr, cptr.size() * sizeof(int64_t)));
+        CUDA_TRY(cudaMemcpy(dg->long_chunk_ptr, cptr.data(), cptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc((void **)&dg->long_chunk_owner, owner.size() * sizeof(int32_t)));
+        CUDA_TRY(cudaMemcpy(dg->long_chunk_owner, owner.data(), owner.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
 }
 
 // Upload the CSR once per (graph, device).  Arrays get 16 trailing elements of padding so tile loads never
@@ -130,6 +163,9 @@ DeviceGraph &device_graph(Graph &g) {
     std::lock_guard<std::recursive_mutex> lock(g.mu);
     for (DeviceGraph *have : g.devs)
         if (have->device == dev) return *have;
+    if (g.device_only && g.col.empty())
+        value_error("this graph was built on device " + std::to_string(g.devs.empty() ? -1 : g.devs[0]->device) +
+                    " and has no host copy; call it with that device current");
     if (!g.host_pinned && env_int64("CLEORA_B200_PIN_CSR", 1) != 0 && g.nnz() >= (1 << 20)) {
         // page-lock the host CSR once: uploads then run at PCIe speed instead of through the pageable staging path
         auto pin = [](const void *p, size_t bytes) { if (bytes) { if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) cudaGetLastError(); } };
@@ -157,41 +193,42 @@ DeviceGraph &device_graph(Graph &g) {
             CUDA_TRY(cudaMalloc((void **)&dg->hash, g.hash.size() * sizeof(uint64_t)));
             CUDA_TRY(cudaMemcpy(dg->hash, g.hash.data(), g.hash.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
         }
-        {   // long-row schedule (degree skew): rows above the threshold are processed chunk-wise by separate warps.
-            // The default threshold is deliberately high: a chunked f32 sum differs from the reference's sequential
-            // sum by ~sqrt(deg) ulp (measured 1e-5 relative at 30k edges, and that feeds back through 40 iterations on
-            // star-like graphs), so splitting is reserved for hubs whose sequential walk would dominate the launch.
-            const int64_t threshold = env_int64("CLEORA_B200_LONG_ROW", 65536), chunk = env_int64("CLEORA_B200_LONG_CHUNK", 4096);
-            std::vector<int64_t> rows, cptr{0};
-            std::vector<int32_t> owner;
-            for (int64_t r = 0; r < g.n_rows; ++r) {
-                const int64_t deg = g.rowptr[(size_t)r + 1] - g.rowptr[(size_t)r];
-                if (deg > threshold) {
-                    const int64_t nc = (deg + chunk - 1) / chunk;
-                    for (int64_t c = 0; c < nc; ++c) owner.push_back((int32_t)rows.size());
-                    rows.push_back(r);
-                    cptr.push_back(cptr.back() + nc);
-                }
-            }
-            dg->long_threshold = threshold;
-            dg->long_chunk_edges = chunk;
-            dg->n_long = (int64_t)rows.size();
-            dg->n_long_chunks = (int64_t)owner.size();
-            if (!rows.empty()) {
-                CUDA_TRY(cudaMalloc((void **)&dg->long_rows, rows.size() * sizeof(int64_t)));
-                CUDA_TRY(cudaMemcpy(dg->long_rows, rows.data(), rows.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
-                CUDA_TRY(cudaMalloc((void **)&dg->long_chunk_ptr, cptr.size() * sizeof(int64_t)));
-                CUDA_TRY(cudaMemcpy(dg->long_chunk_ptr, cptr.data(), cptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
-                CUDA_TRY(cudaMalloc((void **)&dg->long_chunk_owner, owner.size() * sizeof(int32_t)));
-                CUDA_TRY(cudaMemcpy(dg->long_chunk_owner, owner.data(), owner.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-            }
-        }
+        attach_long_row_schedule(*dg, g.rowptr);
     } catch (...) {
         free_device_graph(dg);
         throw;
     }
     g.devs.push_back(dg);
     return *dg;
+}
+
+// Host arrays of a device-built graph, downloaded on first use by an accessor that needs them.
+void materialize_host(Graph &g) {
+    std::lock_guard<std::recursive_mutex> lock(g.mu);
+    if (!g.device_only || g.devs.empty()) return;
+    DeviceGraph &dg = *g.devs[0];
+    if (g.col.empty() && g.nnz_device > 0) {
+        const size_t nnz = (size_t)g.nnz_device;
+        std::vector<uint32_t> col(nnz);
+        std::vector<float> left(nnz), sym;
+        CUDA_TRY(cudaMemcpy(col.data(), dg.col, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(left.data(), dg.left, nnz * sizeof(float), cudaMemcpyDeviceToHost));
+        if (dg.sym) { sym.resize(nnz); CUDA_TRY(cudaMemcpy(sym.data(), dg.sym, nnz * sizeof(float), cudaMemcpyDeviceToHost)); }
+        g.col.swap(col); g.left.swap(left); g.sym.swap(sym);
+    }
+    if (g.row_sum.empty() && g.n_rows) {
+        g.row_sum.resize((size_t)g.n_rows);
+        CUDA_TRY(cudaMemcpy(g.row_sum.data(), dg.row_sum_all + g.shard_r0, (size_t)g.n_rows * sizeof(float), cudaMemcpyDeviceToHost));
+        g.hash.resize((size_t)g.n_rows);
+        CUDA_TRY(cudaMemcpy(g.hash.data(), dg.hash + g.row_offset, (size_t)g.n_rows * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        g.column_id.assign((size_t)g.n_rows, 0);
+    }
+    if (g.ids.empty() && g.n_rows && dg.orig_ids) {             // entity ids = decimal strings of the integer ids
+        std::vector<uint32_t> orig((size_t)g.n_rows);
+        CUDA_TRY(cudaMemcpy(orig.data(), dg.orig_ids + g.shard_r0, orig.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        g.ids.resize(orig.size());
+        for (size_t i = 0; i < orig.size(); ++i) g.ids[i] = std::to_string(orig[i]);
+    }
 }
 
 const float *values_of(DeviceGraph &dg, int markov) {
@@ -695,6 +732,31 @@ extern "C" int cleora_graph_from_pairs(const uint32_t *u, const uint32_t *v, int
         *out = static_cast<cleora_graph_t *>(g.release());
     });
 }
+extern "C" int cleora_dev_graph_from_pairs(const uint32_t *u, const uint32_t *v, int64_t n_pairs, const char *column_name,
+                                           int shard_rank, int shard_world, int want_sym, void *stream,
+                                           cleora_graph_t **out, int64_t *bounds_out) {
+    return guarded([&] {
+        require_device();
+        std::vector<int64_t> bounds;
+        auto g = build_from_pairs_device(u, v, n_pairs, column_name ? column_name : "node", shard_rank, shard_world,
+                                         want_sym != 0, (cudaStream_t)stream, &bounds);
+        attach_long_row_schedule(*g->devs[0], g->rowptr);
+        if (bounds_out) std::copy(bounds.begin(), bounds.end(), bounds_out);
+        *out = static_cast<cleora_graph_t *>(g.release());
+    });
+}
+extern "C" int cleora_dev_synth_pairs(int kind, int64_t n_nodes, int64_t n_pairs, uint64_t seed, double alpha,
+                                      uint32_t *u, uint32_t *v, void *stream) {
+    return guarded([&] { require_device(); synth_pairs_device(kind, n_nodes, n_pairs, seed, alpha, u, v, (cudaStream_t)stream); });
+}
+extern "C" int cleora_dev_graph_hashes(cleora_graph_t *g, const uint64_t **hash, int64_t *n_hash) {
+    return guarded([&] {
+        DeviceGraph &dg = device_graph(*g);
+        *hash = dg.hash;
+        *n_hash = dg.hash_rows ? dg.hash_rows : (dg.hash ? g->n_rows : 0);
+    });
+}
+extern "C" int64_t cleora_graph_num_entities_global(const cleora_graph_t *g) { return g->device_only ? g->n_global : g->n_rows; }
 extern "C" int cleora_graph_from_csr(const int64_t *rowptr, const uint32_t *col, const float *val_left,
                                      const float *val_sym, const float *row_sum, const uint64_t *entity_hash,
                                      int64_t n_rows, int64_t n_cols, int64_t row_offset, cleora_graph_t **out) {
@@ -736,11 +798,27 @@ extern "C" int cleora_graph_release_device(cleora_graph_t *g) {
         g->devs.clear();
     });
 }
+// Copy the host CSR into the device image again (same buffers: no allocation, no long-row re-scan) -- the per-step
+// "inputs arrive from the host" leg of an end-to-end measurement or of a serving loop that reuses its allocations.
+// Creates the image when the current device has none yet.
+extern "C" int cleora_graph_refresh_device(cleora_graph_t *g, void *stream) {
+    return guarded([&] {
+        DeviceGraph &dg = device_graph(*g);
+        cudaStream_t st = (cudaStream_t)stream;
+        const size_t nnz = (size_t)g->nnz();
+        CUDA_TRY(cudaMemcpyAsync(dg.rowptr, g->rowptr.data(), g->rowptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(dg.col, g->col.data(), nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(dg.left, g->left.data(), nnz * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (dg.hash) CUDA_TRY(cudaMemcpyAsync(dg.hash, g->hash.data(), g->hash.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        std::lock_guard<std::mutex> lock(dg.lazy_mu);
+        if (dg.sym) CUDA_TRY(cudaMemcpyAsync(dg.sym, g->sym.data(), nnz * sizeof(float), cudaMemcpyHostToDevice, st));
+    });
+}
 extern "C" int64_t cleora_graph_num_entities(const cleora_graph_t *g) { return g->n_rows; }
 extern "C" int64_t cleora_graph_num_cols(const cleora_graph_t *g) { return g->n_cols; }
 extern "C" int64_t cleora_graph_num_edges(const cleora_graph_t *g) { return g->nnz(); }
 extern "C" int cleora_graph_copy_csr(const cleora_graph_t *g, int64_t *rowptr, uint32_t *col, float *left, float *sym) {
-    return guarded([&] {
+    return guarded([&] { materialize_host(*const_cast<cleora_graph_t *>(g));
         if (rowptr) std::copy(g->rowptr.begin(), g->rowptr.end(), rowptr);
         if (col) std::copy(g->col.begin(), g->col.end(), col);
         if (left) std::copy(g->left.begin(), g->left.end(), left);
@@ -751,21 +829,22 @@ extern "C" int cleora_graph_copy_csr(const cleora_graph_t *g, int64_t *rowptr, u
     });
 }
 extern "C" int cleora_graph_copy_row_sums(const cleora_graph_t *g, float *out) {
-    return guarded([&] { std::copy(g->row_sum.begin(), g->row_sum.end(), out); });
+    return guarded([&] { materialize_host(*const_cast<cleora_graph_t *>(g)); std::copy(g->row_sum.begin(), g->row_sum.end(), out); });
 }
 extern "C" int cleora_graph_copy_entity_hashes(const cleora_graph_t *g, uint64_t *out) {
-    return guarded([&] { std::copy(g->hash.begin(), g->hash.end(), out); });
+    return guarded([&] { materialize_host(*const_cast<cleora_graph_t *>(g)); std::copy(g->hash.begin(), g->hash.end(), out); });
 }
 extern "C" int cleora_graph_copy_column_ids(const cleora_graph_t *g, uint8_t *out) {
-    return guarded([&] { std::copy(g->column_id.begin(), g->column_id.end(), out); });
+    return guarded([&] { materialize_host(*const_cast<cleora_graph_t *>(g)); std::copy(g->column_id.begin(), g->column_id.end(), out); });
 }
 extern "C" int64_t cleora_graph_entity_ids_nbytes(const cleora_graph_t *g) {
+    try { materialize_host(*const_cast<cleora_graph_t *>(g)); } catch (...) { return 0; }
     int64_t t = 0;
     for (const auto &s : g->ids) t += (int64_t)s.size();
     return t;
 }
 extern "C" int cleora_graph_copy_entity_ids(const cleora_graph_t *g, char *buf, int64_t *offsets) {
-    return guarded([&] {
+    return guarded([&] { materialize_host(*const_cast<cleora_graph_t *>(g));
         int64_t pos = 0;
         offsets[0] = 0;
         for (size_t i = 0; i < g->ids.size(); ++i) {
@@ -778,6 +857,7 @@ extern "C" int cleora_graph_copy_entity_ids(const cleora_graph_t *g, char *buf, 
 extern "C" int cleora_graph_set_entity_ids(cleora_graph_t *g, const char *buf, const int64_t *offsets, int64_t n) {
     return guarded([&] {
         if (n != g->n_rows) value_error("entity_ids must keep its length (" + std::to_string(g->n_rows) + ")");
+        materialize_host(*g);
         std::lock_guard<std::recursive_mutex> lock0(g->mu);
         g->ids.resize((size_t)n);
         g->hash.resize((size_t)n);
@@ -811,6 +891,7 @@ extern "C" const char *cleora_graph_col_name(const cleora_graph_t *g, int which)
 extern "C" int cleora_graph_col_id(const cleora_graph_t *g, int which) { return which ? g->desc.col_b_id : g->desc.col_a_id; }
 extern "C" int64_t cleora_graph_find_entity(const cleora_graph_t *cg, const char *id, int64_t id_len) {
     Graph *g = const_cast<cleora_graph_t *>(cg);
+    try { materialize_host(*g); } catch (...) { return -1; }
     std::lock_guard<std::recursive_mutex> lock(g->mu);      // the index is built lazily; lookups may come from several threads
     if (g->id_index.empty() && !g->ids.empty())
         for (size_t i = 0; i < g->ids.size(); ++i) g->id_index.emplace(g->ids[i], (int64_t)i);   // first wins

@@ -5,8 +5,10 @@
 #include <atomic>
 #include <cstdint>
 #include <climits>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <vector>
 
 namespace cleora {
 
@@ -27,6 +29,11 @@ struct DeviceGraph {
     int64_t *long_chunk_ptr = nullptr;     // [n_long + 1] first chunk of each long row
     int32_t *long_chunk_owner = nullptr;   // [n_long_chunks] index into long_rows
     float *rsum_left = nullptr, *rsum_sym = nullptr;   // A*1 per Markov type, built on first pipelined use
+    // device-built graphs (graph_dev.cu): row sums of ALL entities, original integer ids by entity index, entity count
+    // of the whole graph, and the number of entries in `hash` (n, or the padded row count of the gathered layout)
+    float *row_sum_all = nullptr;
+    uint32_t *orig_ids = nullptr;
+    int64_t n_global = 0, hash_rows = 0;
     std::mutex lazy_mu;                    // guards the lazily built members (sym, rsum_*)
 };
 
@@ -104,6 +111,13 @@ void launch_sq_diff_sum(const float *a, const float *b, int64_t n, bool f64_diff
 void launch_build_transform(const double *V, const double *w, int64_t d, int64_t dout, float *T, cudaStream_t st);
 void launch_scale_f64(double *v, int64_t n, double factor, cudaStream_t st);
 void launch_f64_to_f32(const double *in, float *out, int64_t n, cudaStream_t st);
+// Device-side integer ingest and synthetic pair generators (graph_dev.cu).
+struct Graph;
+std::unique_ptr<Graph> build_from_pairs_device(const uint32_t *u, const uint32_t *v, int64_t n_pairs,
+                                               const std::string &column_name, int rank, int world, bool want_sym,
+                                               cudaStream_t st, std::vector<int64_t> *bounds_out);
+void synth_pairs_device(int kind, int64_t n_nodes, int64_t n_pairs, uint64_t seed, double alpha, uint32_t *u, uint32_t *v,
+                        cudaStream_t st);
 // Cholesky whitening (chol_whiten.cu): T = L^-T of cov = L L^T as f32; status[0] raised when cov is not safely SPD.
 bool chol_whiten_supported(int64_t d);
 void launch_chol_whiten(const double *cov, int64_t d, float *T, int *status, cudaStream_t st);

@@ -41,7 +41,12 @@ struct Graph {
     std::recursive_mutex mu;              // guards the lazy caches (devs and their lazily built members, id_index):
                                           // ctypes drops the GIL, so two Python threads may share one graph
     bool host_pinned = false;             // CSR arrays page-locked (cudaHostRegister) for fast (re-)uploads
-    int64_t nnz() const { return (int64_t)col.size(); }
+    // Graphs built on the device (graph_dev.cu) keep col / left / sym / row_sum / hash in HBM only (host `rowptr` is
+    // filled); the host accessors download them on first use (abi.cu: materialize_host).
+    bool device_only = false;
+    int64_t nnz_device = 0;               // nnz while the host arrays are not materialised
+    int64_t n_global = 0, shard_r0 = 0;   // device-built shards: entity count of the whole graph, first global row
+    int64_t nnz() const { return device_only && col.empty() ? nnz_device : (int64_t)col.size(); }
 };
 
 struct BuildError {

@@ -108,6 +108,26 @@ class SparseMatrix:
         return SparseMatrix._adopt(h)
 
     @staticmethod
+    def from_edge_arrays_device(src, dst, column_name: str = "node", shard_rank: int = 0, shard_world: int = 1,
+                                want_sym: bool = True, stream: int = 0) -> "SparseMatrix":
+        """``from_edge_arrays`` on the GPU: ``src`` / ``dst`` are DEVICE arrays of 32-bit ids on the current device
+        (anything with ``data_ptr()`` and ``numel()``, e.g. torch int32 / uint32 tensors).  The CSR is built and kept in
+        HBM (``include/cleora_b200.h``: cleora_dev_graph_from_pairs); with ``shard_world > 1`` only the row block
+        ``shard_rank`` is built, in the padded gathered layout of ``cleora_b200.sharded``.  ``.shard_bounds`` holds the
+        row partition."""
+        n_pairs = int(src.numel())
+        if int(dst.numel()) != n_pairs:
+            raise ValueError("src and dst must have the same length")
+        h = C.c_void_p()
+        bounds = np.zeros(int(shard_world) + 1, np.int64)
+        check(_lib.lib().cleora_dev_graph_from_pairs(src.data_ptr(), dst.data_ptr(), n_pairs, column_name.encode("utf-8"),
+                                                     int(shard_rank), int(shard_world), 1 if want_sym else 0, stream,
+                                                     C.byref(h), ptr(bounds, _lib.c_i64p)))
+        sm = SparseMatrix._adopt(h)
+        sm.shard_bounds = bounds
+        return sm
+
+    @staticmethod
     def from_csr(rowptr, col, val_left, val_sym=None, row_sum=None, entity_hash=None, n_cols=None,
                  row_offset: int = 0) -> "SparseMatrix":
         """Adopt a prebuilt CSR (a full graph or a row shard of one)."""

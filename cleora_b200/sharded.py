@@ -74,6 +74,29 @@ class Shard:
         self.hash_padded = hp
 
     @classmethod
+    def from_device_pairs(cls, u, v, rank: int, world: int, want_sym: bool = False, column_name: str = "node") -> "Shard":
+        """This rank's row block built on the GPU straight from the (device-resident) pair arrays -- every rank passes
+        the same pairs; nothing of the CSR touches the host (cleora_dev_graph_from_pairs)."""
+        self = cls.__new__(cls)
+        g = SparseMatrix.from_edge_arrays_device(u, v, column_name, rank, world, want_sym)
+        L = _lib.lib()
+        self.graph, self.rank, self.world = g, rank, world
+        self.bounds = np.asarray(g.shard_bounds, np.int64)
+        self.n = int(L.cleora_graph_num_entities_global(g._handle()))
+        self.block = int(np.max(np.diff(self.bounds))) if self.n else 0
+        self.r0, self.r1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.n_local = self.r1 - self.r0
+        self.nnz_local = g.num_edges
+        self.nnz = None                                   # global nnz: sum over ranks (bench all-reduces it)
+        self.n_pad = self.block * world
+        hp, nh = C.c_void_p(), C.c_int64()
+        check(L.cleora_dev_graph_hashes(g._handle(), C.byref(hp), C.byref(nh)))
+        self.hash_padded = None
+        self.hash_ptr = hp.value                          # device pointer, n_pad entries (library-owned)
+        assert world == 1 or int(nh.value) == self.n_pad
+        return self
+
+    @classmethod
     def from_matrix(cls, g: SparseMatrix, rank: int, world: int) -> "Shard":
         rowptr, col, left, sym = g._csr()
         return cls(rowptr, col, left, sym, g.entity_hashes(), rank, world)
@@ -190,6 +213,16 @@ class CudaBackend:
         self.torch.cuda.synchronize()
 
 
+class _DevPtr:
+    """A raw device address with the one method the backend needs."""
+
+    def __init__(self, address: int):
+        self._a = int(address)
+
+    def data_ptr(self) -> int:
+        return self._a
+
+
 class _CudaArray:
     """__cuda_array_interface__ shim so torch can view library-allocated (IPC-exportable) device memory."""
 
@@ -281,7 +314,10 @@ class ShardedEmbedder:
         self.scalar = be.empty((1,), torch.float64)
         self.status = be.empty((1,), torch.int32)               # raised by the Cholesky whitening kernel
         self.status.zero_()
-        self.hash_pad = be.from_numpy(s.hash_padded.view(np.int64)) if s.n_pad else be.empty((1,), torch.int64)
+        if getattr(s, "hash_ptr", None):
+            self.hash_pad = _DevPtr(s.hash_ptr)                                # device-built shard: hashes already in HBM
+        else:
+            self.hash_pad = be.from_numpy(s.hash_padded.view(np.int64)) if s.n_pad else be.empty((1,), torch.int64)
         self.phase_ms = {}
         if s.n_pad:
             self.x_full.zero_()
@@ -642,21 +678,21 @@ def bench(args, w, name, gen_pairs, spmm_bytes, measured_peaks, ClockSampler):
     tot = timers.totals()
     phases = torch.tensor([tot.get(k, 0.0) for k in ("spmm", "stats", "eigh", "apply", "gather")], device="cuda")
     dist.all_reduce(phases, op=dist.ReduceOp.MAX)
-    # e2e: host CSR shard -> upload -> loop -> this rank's rows of the result in (pinned) host memory.  The full result
-    # is the concatenation of the ranks' blocks; every rank writes its own block, as a sharded consumer would.
+    # e2e: host CSR shard -> device (every step, same device buffers) -> loop -> this rank's rows of the result in
+    # pinned host memory.  The full result is the concatenation of the ranks' blocks; every rank writes its own block,
+    # as a sharded consumer would.  Timed per rank from a common barrier; the slowest rank counts.
     from . import pinned_empty
     own = pinned_empty((max(shard.block, 1), d), np.float32)
     own_t = torch.from_numpy(own)
     e2e_t = []
     for i in range(1 + args.e2e_steps):
-        check(em.be.L.cleora_graph_release_device(shard.graph._handle()))
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
+        check(em.be.L.cleora_graph_refresh_device(shard.graph._handle(), em.be.stream()))
         step()
         own_t.copy_(em._own(em.x_full), non_blocking=True)
         torch.cuda.synchronize()
-        dist.barrier()
         if i > 0:
             e2e_t.append(time.perf_counter() - t0)
     res = own[:shard.n_local]
@@ -675,14 +711,19 @@ def bench(args, w, name, gen_pairs, spmm_bytes, measured_peaks, ClockSampler):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "nodes": n, "edges": E, "nnz": nnz, "d": d, "iters": iters,
                        "whiten": bool(args.whiten), "pipeline_whiten": bool(piped),
+                       "inner_whitening": ("Cholesky factor, computed redundantly on every rank (no broadcast); PCA eigh "
+                                           "on rank 0 + broadcast for the last iterate" if em.be.chol_enabled(d)
+                                           else "PCA eigh on rank 0 + broadcast every iteration"),
                        "parallelism": f"row-shard x{world} (nnz-balanced)",
-                       "collectives": "NCCL all-gather of X blocks per iteration; all-reduce of d+d*d f64; T broadcast",
+                       "collectives": "NCCL all-gather of X blocks per iteration; all-reduce of d+d*d f64",
                        "l2_flush": "inputs exceed the 126 MB L2"},
             "nnz_per_s": nnz * iters / (ms_step * 1e-3),
             "e2e": {"value": E * iters / float(e2e.item()), "unit": "edges/s",
                     "h2d_bytes_per_step": int(8 * (shard.n_local + 1) + 8 * shard.nnz_local + 8 * n),
                     "d2h_bytes_per_step": int(4 * shard.n_local * d), "ms_per_step": 1e3 * float(e2e.item()),
-                    "note": "per-rank bytes; each rank uploads its CSR shard and downloads its own rows of the result"},
+                    "samples": len(e2e_t),
+                    "note": "per-rank bytes; each rank re-copies its CSR shard host->device and downloads its own rows "
+                            "of the result every step; X0 comes from the init kernel; max over ranks"},
             "gpu_launches": int(launches.item()),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel (K1), per GPU", "achieved": achieved, "peak": peak,
@@ -690,6 +731,7 @@ def bench(args, w, name, gen_pairs, spmm_bytes, measured_peaks, ClockSampler):
                          "ms_per_launch": spmm_ms},
             "phase_ms_per_iter": {k: float(phases[i].item()) / (iters * args.steps)
                                   for i, k in enumerate(("spmm", "stats", "eigh", "apply", "gather"))},
+            "phase_note": "max over ranks; eigh (inner: Cholesky kernel) and gather run on side streams beside spmm / stats",
             "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)

@@ -71,10 +71,33 @@ int cleora_graph_from_files(const char *const *paths, int64_t n_paths, const cha
                             int64_t hyperedge_trim_n, cleora_graph_t **out);
 /* Direct integer ingest: the graph that `from_iterator(("{u} {v}" for u,v in pairs),
  * "complex::reflexive::<name>")` builds, without strings: entity index = first appearance, entity id =
- * decimal string of the integer, every pair adds 1/4+1/4 to M[u,v], M[v,u], M[u,u], M[v,v].  u == v pairs are
- * legal (they add 1 to M[u,u]). */
+ * decimal string of the integer, every pair adds 1/4+1/4 to M[u,v], M[v,u], M[u,u], M[v,v] and 1 to both row
+ * sums.  u == v pairs are legal: all four ordered pairs of the line are (u,u), so they add 8 * 1/4 = 2 to M[u,u] and
+ * 2 to row_sum[u] (src/sparse_matrix_builder.rs:170-233). */
 int cleora_graph_from_pairs(const uint32_t *u, const uint32_t *v, int64_t n_pairs, const char *column_name,
                             cleora_graph_t **out);
+/* The same ingest on the GPU (graph_dev.cu): `u`, `v` are DEVICE arrays on the current device; the CSR is built and
+ * kept in HBM (no host copy: the 1.5 B-edge configuration has 24 GB of it; host accessors download on demand), bit for
+ * bit the graph cleora_graph_from_pairs builds -- entity order, merged values, row sums, hashes.  shard_world > 1
+ * builds ONE ROW SHARD directly: rows are split into shard_world contiguous blocks balanced by entry count
+ * (`bounds_out`, int64[shard_world + 1], the same on every rank given the same pairs), this call keeps block
+ * `shard_rank` with its column indices remapped to the padded gathered layout (owner * block + offset in owner,
+ * block = largest block), n_cols = shard_world * block, row_offset = shard_rank * block.  want_sym == 0 skips the
+ * symmetric values (4 B/nnz).  Ids must be dense (max id < 2^31).  Synchronises `stream` a few times (scalar counts). */
+int cleora_dev_graph_from_pairs(const uint32_t *u, const uint32_t *v, int64_t n_pairs, const char *column_name,
+                                int shard_rank, int shard_world, int want_sym, void *stream, cleora_graph_t **out,
+                                int64_t *bounds_out);
+/* Synthetic pair streams for benchmarks, generated on the device with a counter-based RNG (pair i depends only on
+ * (seed, i): every rank of a sharded run regenerates the same stream locally).  kind 0: endpoints i.i.d. uniform
+ * (Erdos-Renyi multigraph); kind 1: Chung-Lu, endpoint weights (i + 10)^-alpha, ids decoupled from the weight rank by a
+ * fixed pseudo-random permutation.  u != v always.  `u`, `v`: device uint32[n_pairs]. */
+int cleora_dev_synth_pairs(int kind, int64_t n_nodes, int64_t n_pairs, uint64_t seed, double alpha, uint32_t *u,
+                           uint32_t *v, void *stream);
+/* Device pointer to the entity hashes cleora_dev_init reads: one per row of the (padded, for a device-built shard)
+ * gathered matrix.  Uploads the graph if needed. */
+int cleora_dev_graph_hashes(cleora_graph_t *g, const uint64_t **hash, int64_t *n_hash);
+/* Entity count of the whole graph (== num_entities except for a device-built shard). */
+int64_t cleora_graph_num_entities_global(const cleora_graph_t *g);
 /* Adopt a prebuilt CSR (copied).  `n_rows` rows over `n_cols` columns; for a full graph n_rows == n_cols.  A
  * row shard of a larger graph has n_rows < n_cols and `row_offset` = global index of its first row (used by
  * the residual mix and by init).  `val_sym`, `row_sum`, `entity_hash` may be NULL. */
@@ -82,8 +105,11 @@ int cleora_graph_from_csr(const int64_t *rowptr, const uint32_t *col, const floa
                           const float *row_sum, const uint64_t *entity_hash, int64_t n_rows, int64_t n_cols,
                           int64_t row_offset, cleora_graph_t **out);
 void cleora_graph_destroy(cleora_graph_t *g);
-/* Drop the cached device copy (CSR stays on the host). */
+/* Drop the cached device copies (CSR stays on the host). */
 int cleora_graph_release_device(cleora_graph_t *g);
+/* Copy the host CSR into the current device's image again on `stream` (a cudaStream_t), reusing its buffers; uploads
+ * it first if the device has no image yet.  For callers whose inputs arrive from the host every step. */
+int cleora_graph_refresh_device(cleora_graph_t *g, void *stream);
 
 /* --- introspection (getters of the pyclass: src/sparse_matrix.rs:56-66, src/lib.rs:175-240,254-318) ------- */
 int64_t cleora_graph_num_entities(const cleora_graph_t *g); /* rows  (len(entity_ids)) */

@@ -61,6 +61,8 @@ def lib():
         L.orc_graph_build.restype = C.c_void_p
         L.orc_graph_build.argtypes = [C.c_char_p, _i64p, C.c_int64, C.c_char_p, C.c_int64, C.c_char_p, C.c_size_t]
         L.orc_graph_free.argtypes = [C.c_void_p]
+        L.orc_graph_from_pairs.restype = C.c_void_p
+        L.orc_graph_from_pairs.argtypes = [_u32p, _u32p, C.c_int64, C.c_char_p]
         for name, rt in [("n", C.c_int64), ("nnz", C.c_int64), ("rowptr", C.c_void_p), ("col", C.c_void_p),
                          ("left", C.c_void_p), ("sym", C.c_void_p), ("row_sum", C.c_void_p),
                          ("hash", C.c_void_p), ("column_id", C.c_void_p)]:
@@ -156,6 +158,32 @@ def build_graph(lines, columns: str, hyperedge_trim_n: int = 16) -> OracleGraph:
     finally:
         L.orc_graph_free(h)
     return g
+
+
+def graph_from_pairs(src, dst, column_name: str = "node") -> OracleGraph:
+    """The graph ``build_graph((f"{u} {v}" ...), "complex::reflexive::name")`` builds, from the id arrays
+    (``orc_graph_from_pairs``).  ``entity_ids`` is None (the ids are the decimal strings, not materialised)."""
+    u = np.ascontiguousarray(src, np.uint32)
+    v = np.ascontiguousarray(dst, np.uint32)
+    assert u.shape == v.shape and u.ndim == 1
+    L = lib()
+    h = L.orc_graph_from_pairs(u, v, u.shape[0], column_name.encode())
+    try:
+        n, nnz = L.orc_graph_n(h), L.orc_graph_nnz(h)
+
+        def arr(ptr, count, dt):
+            if count == 0:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(count,)).copy()
+
+        return OracleGraph(
+            arr(L.orc_graph_rowptr(h), n + 1, np.int64) if n else np.zeros(1, np.int64),
+            arr(L.orc_graph_col(h), nnz, np.uint32), arr(L.orc_graph_left(h), nnz, np.float32),
+            arr(L.orc_graph_sym(h), nnz, np.float32), arr(L.orc_graph_row_sum(h), n, np.float32),
+            arr(L.orc_graph_hash(h), n, np.uint64), arr(L.orc_graph_column_id(h), n, np.uint8), None,
+            column_name, column_name, 0, 1)
+    finally:
+        L.orc_graph_free(h)
 
 
 # ------------------------------------------------------------------------------------------------ Rust-side compute

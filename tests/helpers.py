@@ -50,3 +50,19 @@ def elem_rel_err(a, b, floor=0.0):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return np.abs(a - b) / np.maximum(np.abs(b), floor if floor > 0 else 1e-300)
+
+
+def procrustes_err(a, b):
+    """|aQ - b| / |b| with Q = argmin over orthogonal matrices."""
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    u, _, vt = np.linalg.svd(a64.T @ b64)
+    return float(np.max(np.abs(a64 @ (u @ vt) - b64)) / np.max(np.abs(b64)))
+
+
+def gram_err(a, b, pairs=20000, seed=0):
+    """max |<a_i, a_j> - <b_i, b_j>| over sampled row pairs, relative to the largest reference inner product."""
+    rs = np.random.default_rng(seed)
+    i, j = rs.integers(0, a.shape[0], pairs), rs.integers(0, a.shape[0], pairs)
+    ga = np.einsum("ij,ij->i", a[i].astype(np.float64), a[j].astype(np.float64))
+    gb = np.einsum("ij,ij->i", b[i].astype(np.float64), b[j].astype(np.float64))
+    return float(np.max(np.abs(ga - gb)) / np.max(np.abs(gb)))

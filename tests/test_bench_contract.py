@@ -21,6 +21,7 @@ def test_reference_arm_json_line():
     assert j["impl"] == "reference" and j["unit"] == "edges/s" and j["value"] > 0
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["config"]["workload"] == "er-50k-1m-d128"
+    assert j["product_library_loaded"] is False          # the CPU arm builds its graph with the oracle's own ingest
 
 
 def test_workload_generators_are_deterministic():

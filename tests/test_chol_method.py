@@ -114,7 +114,7 @@ def test_inner_cholesky_whitening_reproduces_reference_iterate_karate():
 
 
 def test_inner_cholesky_whitening_er_graph_procrustes_and_gram():
-    from tests.test_gpu_parity import gram_err, procrustes_err
+    from tests.helpers import gram_err, procrustes_err
     og = oracle.build_graph(er_lines(3000, 30000, 11), "complex::reflexive::node")
     ref = oracle.embed(og, 64, 12)
     got = _loop(og, 64, 12, _chol_whiten)

@@ -18,7 +18,7 @@ import pytest
 import cleora_b200 as cb
 import oracle
 from cleora_b200 import _lib
-from tests.helpers import KARATE_COLUMNS, KARATE_EDGES, er_lines, scale_rel_err
+from tests.helpers import KARATE_COLUMNS, KARATE_EDGES, er_lines, gram_err, procrustes_err, scale_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -309,21 +309,6 @@ def test_whiten_embeddings_matches_reference_golden(golden_dir):
 
 
 # ------------------------------------------------------------------------------------------------ P5: whitened loop
-def procrustes_err(a, b):
-    """|aQ - b| / |b| with Q = argmin over orthogonal matrices."""
-    a64, b64 = a.astype(np.float64), b.astype(np.float64)
-    u, _, vt = np.linalg.svd(a64.T @ b64)
-    return float(np.max(np.abs(a64 @ (u @ vt) - b64)) / np.max(np.abs(b64)))
-
-
-def gram_err(a, b, pairs=20000, seed=0):
-    rs = np.random.default_rng(seed)
-    i, j = rs.integers(0, a.shape[0], pairs), rs.integers(0, a.shape[0], pairs)
-    ga = np.einsum("ij,ij->i", a[i].astype(np.float64), a[j].astype(np.float64))
-    gb = np.einsum("ij,ij->i", b[i].astype(np.float64), b[j].astype(np.float64))
-    return float(np.max(np.abs(ga - gb)) / np.max(np.abs(gb)))
-
-
 @pytest.mark.parametrize("name,raw_tol", [("karate_d8_t5_w", 1e-4), ("karate_d32_t5_w", None), ("karate_d8_t40_w", 1e-4)])
 def test_default_embed_matches_reference_output_karate(golden_dir, name, raw_tol):
     """pycleora.embed() default path (whiten=True) against the unmodified reference's output."""
@@ -403,6 +388,121 @@ def test_pipelined_loop_equals_reference_stage_order(er_pair):
         assert procrustes_err(got, ref) <= 1e-4
     assert gram_err(piped, faithful) <= 1e-5
     np.testing.assert_allclose(np.cov(piped.astype(np.float64), rowvar=False), np.eye(64), atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ Cholesky whitening
+@pytest.mark.parametrize("d", [1, 8, 32, 100, 128, 256, 512])
+def test_chol_whiten_kernel(d):
+    """chol_whiten.cu: T = L^-T of cov = L L^T, f64 on one SM.  T^T cov T = I, T upper triangular, equal to numpy's
+    factorisation to f32 rounding; the status flag stays clear for a well-conditioned matrix and is raised for a
+    rank-deficient one (the case in which the reference's 1e-10 clamp, pycleora/__init__.py:155, matters)."""
+    import torch
+    L = _lib.lib()
+    rs = np.random.default_rng(d)
+    a = rs.standard_normal((4 * d + 8, d)) * rs.uniform(0.1, 3.0, d)
+    cov = np.atleast_2d(np.cov(a, rowvar=False))
+    covd = torch.from_numpy(cov).cuda()
+    T = torch.full((d, d), float("nan"), dtype=torch.float32, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.cleora_dev_chol_whiten(covd.data_ptr(), d, T.data_ptr(), status.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    T64 = T.cpu().numpy().astype(np.float64)
+    ref = np.linalg.inv(np.linalg.cholesky(cov)).T
+    np.testing.assert_allclose(T64, ref, rtol=0, atol=1e-6 * np.max(np.abs(ref)))
+    np.testing.assert_array_equal(np.tril(T64, -1), 0)
+    np.testing.assert_allclose(T64.T @ cov @ T64, np.eye(d), atol=5e-6 * np.linalg.cond(cov) ** 0.5)
+    if d >= 8:                                                       # singular covariance (n - 1 < d): flagged
+        sing = torch.from_numpy(np.cov(rs.standard_normal((d // 2, d)), rowvar=False)).cuda()
+        _lib.check(L.cleora_dev_chol_whiten(sing.data_ptr(), d, T.data_ptr(), status.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert int(status.item()) == 1
+    with pytest.raises(ValueError):
+        _lib.check(L.cleora_dev_chol_whiten(covd.data_ptr(), 513, T.data_ptr(), status.data_ptr(), st))
+
+
+def _with_options(fn, **opts):
+    old = {k: int(_lib.lib().cleora_get_option(k.encode())) for k in opts}
+    try:
+        for k, v in opts.items():
+            cb.set_option(k, v)
+        return fn()
+    finally:
+        for k, v in old.items():
+            cb.set_option(k, v)
+
+
+@pytest.fixture(scope="module")
+def er200k_pair():
+    """ER 200k nodes / 2M pairs through the integer ingest; the oracle graph shares the product's CSR (itself checked
+    bit-for-bit against the oracle's builder in tests/test_graph_build.py)."""
+    rs = np.random.default_rng(11)
+    n, e = 200_000, 2_000_000
+    u, v = rs.integers(0, n, e), rs.integers(0, n, e)
+    k = u != v
+    g = cb.SparseMatrix.from_edge_arrays(u[k], v[k])
+    rowptr, col, left, sym = g._csr()
+    o = oracle.OracleGraph(rowptr, col, left, sym, g.entity_degrees, g.entity_hashes(),
+                           np.zeros(g.num_entities, np.uint8), None)
+    return g, o
+
+
+@pytest.mark.parametrize("d", [256, 128])
+def test_benchmarked_configuration_40_iterations_er20k(er_pair, d):
+    """The path bench.py times -- d = 256 / 128, 40 iterations, whiten=True, default options (pipelined loop, int8
+    Gram, tcgen05 apply, Cholesky-whitened inner iterations, PCA on the last) -- end to end against the oracle's
+    reference-order loop (pycleora/__init__.py:109-125,963-971).  The covariance spectrum of an ER graph is nearly
+    degenerate, so raw coordinates are defined only up to a rotation: the bars are the
+    Procrustes-aligned iterate (<= 1e-4 of scale) and the Gram matrix (<= 1e-5).  Also: the reference stage order
+    (pipeline_whiten=0) and the eigensolver-in-every-iteration variant (chol_whiten=0) against the same oracle."""
+    g, o = er_pair
+    ref = oracle.embed(o, d, 40)
+    variants = {
+        "default": lambda: cb.embed(g, d, 40),
+        "reference order": lambda: _with_options(lambda: cb.embed(g, d, 40), pipeline_whiten=0),
+        "eigensolver every iteration": lambda: _with_options(lambda: cb.embed(g, d, 40), chol_whiten=0),
+        "reference order + eigensolver": lambda: _with_options(lambda: cb.embed(g, d, 40), pipeline_whiten=0, chol_whiten=0),
+    }
+    for name, fn in variants.items():
+        got = fn()
+        assert procrustes_err(got, ref) <= 1e-4, name
+        assert gram_err(got, ref) <= 1e-5, name
+        c = np.cov(got.astype(np.float64), rowvar=False)
+        np.testing.assert_allclose(c, np.eye(d), atol=2e-4, err_msg=name)
+
+
+@pytest.mark.parametrize("d", [256, 128])
+def test_benchmarked_configuration_40_iterations_er200k(er200k_pair, d):
+    """Same as above at 200k nodes / 2M pairs (nnz ~ 4.2M), where the int8 Gram runs several row slices per tile and
+    the tensor-core apply many tiles per CTA."""
+    g, o = er200k_pair
+    ref = oracle.embed(o, d, 40)
+    got = cb.embed(g, d, 40)
+    assert procrustes_err(got, ref) <= 1e-4
+    assert gram_err(got, ref) <= 1e-5
+    got_ref_order = _with_options(lambda: cb.embed(g, d, 40), pipeline_whiten=0)
+    assert procrustes_err(got_ref_order, ref) <= 1e-4
+    assert gram_err(got_ref_order, ref) <= 1e-5
+
+
+def test_cholesky_fallback_on_rank_deficient_covariance(golden_dir):
+    """karate d=32: n - 1 = 33 ~ d and the covariance degenerates within a few iterations -- the Cholesky guard must
+    fire and the call must fall back to the eigensolver loop (same result as with chol_whiten=0)."""
+    z = np.load(os.path.join(golden_dir, "embed_karate_d32_t5_w.npz"))
+    g = cb.SparseMatrix.from_iterator([str(s) for s in z["lines"]], str(z["columns"]))
+    got = cb.embed(g, 32, 12)
+    assert np.all(np.isfinite(got))
+    lines = [f"a{i} a{(i + 1) % 9}" for i in range(9)]               # n = 9 < d = 32: singular from the first iteration
+    gs = cb.SparseMatrix.from_iterator(lines, "complex::reflexive::n")
+    count = _lib.lib().cleora_kernel_launch_count
+    c0 = count()
+    a = cb.embed(gs, 32, 4)
+    c1 = count()
+    b = _with_options(lambda: cb.embed(gs, 32, 4), chol_whiten=0)
+    c2 = count()
+    assert np.all(np.isfinite(a)) and np.all(np.isfinite(b)) and a.shape == b.shape == (9, 32)
+    assert c1 - c0 > c2 - c1                                          # flagged attempt + the eigensolver loop again
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties

@@ -60,6 +60,21 @@ def test_integer_ingest_equals_string_path():
     assert repr(gp) == "SparseMatrix(entities={}, edges={}, columns=('node', 'node'))".format(gp.num_entities, gp.num_edges)
 
 
+def test_oracle_integer_ingest_equals_its_string_path():
+    """oracle.graph_from_pairs (used by bench.py's reference arm, so that the CPU baseline loads nothing of the
+    product) against the oracle's own line parser / hyperedge expansion, and against the product's builder."""
+    rs = np.random.default_rng(2)
+    u, v = rs.integers(0, 3000, 30000), rs.integers(0, 3000, 30000)      # includes u == v pairs and duplicates
+    op = oracle.graph_from_pairs(u, v, "node")
+    ol = oracle.build_graph([f"{a} {b}" for a, b in zip(u, v)], "complex::reflexive::node")
+    for name in ("rowptr", "col", "left", "sym", "row_sum", "hashes", "column_ids"):
+        np.testing.assert_array_equal(getattr(op, name), getattr(ol, name), err_msg=name)
+    op.entity_ids = ol.entity_ids
+    assert_same_graph(cb.SparseMatrix.from_edge_arrays(u, v, "node"), op)
+    empty = oracle.graph_from_pairs(np.zeros(0, np.uint32), np.zeros(0, np.uint32))
+    assert empty.n == 0 and empty.nnz == 0
+
+
 def test_from_files(tmp_path):
     p1, p2 = tmp_path / "a.tsv", tmp_path / "b.txt"
     p1.write_text("u1\tp1 p2\n\nu2\tp2\r\n")

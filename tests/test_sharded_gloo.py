@@ -201,7 +201,7 @@ def test_sharded_whitened_loop_matches_oracle(world):
 def test_sharded_pipelined_choreography_matches_oracle(world):
     """d=32 makes the default configuration eligible for the pipelined loop (eigensolve / gather on side streams,
     W = A Y before T is known): same result as the reference-order oracle up to rounding (Gram / Procrustes)."""
-    from tests.test_gpu_parity import gram_err, procrustes_err
+    from tests.helpers import gram_err, procrustes_err
     kw = dict(feature_dim=32, num_iterations=5)
     out = run_sharded(world, (ER[0], ER[1], kw))
     ref = oracle.embed(oracle.build_graph(ER[0], ER[1]), **kw)

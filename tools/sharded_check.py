@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cleora_b200 as cb  # noqa: E402
 from cleora_b200 import sharded  # noqa: E402
 from tests.helpers import er_lines  # noqa: E402
-from tests.test_gpu_parity import gram_err, procrustes_err  # noqa: E402
+from tests.helpers import gram_err, procrustes_err  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
