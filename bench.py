@@ -34,6 +34,20 @@ WORKLOADS = {
     # name: (nodes, input edges, d, generator, rng seed)   -- SURVEY.md 8d
     "er-1m-20m-d256": dict(n=1_000_000, e=20_000_000, d=256, kind="er", seed=1),
     "products-2.4m-62m-d256": dict(n=2_449_029, e=61_859_140, d=256, kind="chunglu", seed=2, alpha=0.5),
+    # BASELINE.json configs[4]: Twitter-2010-shaped, 41.65M nodes / 1.468B edges, Chung-Lu with degree
+    # exponent ~2.2 (endpoint weight (i+10)^-0.833), d=128.  Too large for the numpy generator + host builder inside a
+    # bench run: the pair stream is generated ON THE DEVICE (counter-based RNG, cleora_dev_synth_pairs) and the CSR is
+    # built on the device (cleora_dev_graph_from_pairs); `cpu_sample` = the CPU arms run on a 1/16-scale graph of the
+    # same family.  twitter-5m-183m-d128 is the 1/8-scale member used for quick checks.
+    "twitter-41m-1.5b-d128": dict(n=41_652_230, e=1_468_365_182, d=128, kind="chunglu", seed=5, alpha=0.833,
+                                  device_gen=True, cpu_sample=16),
+    "twitter-5m-183m-d128": dict(n=5_206_528, e=183_545_648, d=128, kind="chunglu", seed=5, alpha=0.833,
+                                 device_gen=True, cpu_sample=4),
+    # BASELINE.json configs[3]: 10M hyperedge lines over a 1M-product vocabulary, one
+    # `complex::reflexive::product` column (clique expansion, n = 1M), size 1 + Poisson(3) capped at 16 (no trimming),
+    # members Zipf(1.0), d=512.  "edges" = hyperedge lines.  hyper-100k-1m-d512 is the 1/10-scale member.
+    "hyper-1m-10m-d512": dict(n=1_000_000, e=10_000_000, d=512, kind="hyper", seed=3, cpu_sample=10),
+    "hyper-100k-1m-d512": dict(n=100_000, e=1_000_000, d=512, kind="hyper", seed=3, cpu_sample=4),
     "er-200k-4m-d256": dict(n=200_000, e=4_000_000, d=256, kind="er", seed=1),
     "er-50k-1m-d128": dict(n=50_000, e=1_000_000, d=128, kind="er", seed=1),
 }
@@ -55,6 +69,65 @@ def gen_pairs(w):
         v = np.searchsorted(cdf, rs.random(e)).astype(np.int64)
         perm = rs.permutation(n)          # decouple node id from weight rank
         u, v = perm[u], perm[v]
+    keep = u != v
+    return u[keep].astype(np.uint32), v[keep].astype(np.uint32)
+
+
+def gen_hyperedges(w, scale=1):
+    """Hyperedge lines as (members uint32, offsets int64): sizes 1 + Poisson(3) capped at 16, members Zipf(1.0) over the
+    vocabulary (inverse CDF), ids decoupled from the popularity rank by a random permutation."""
+    rs = np.random.default_rng(w["seed"])
+    vocab, lines = max(2, w["n"] // scale), max(1, w["e"] // scale)
+    k = np.minimum(1 + rs.poisson(3.0, lines), 16)
+    offsets = np.zeros(lines + 1, np.int64)
+    np.cumsum(k, out=offsets[1:])
+    cdf = np.cumsum(1.0 / np.arange(1, vocab + 1))
+    cdf /= cdf[-1]
+    perm = rs.permutation(vocab)
+    members = perm[np.searchsorted(cdf, rs.random(int(offsets[-1])))].astype(np.uint32)
+    return members, offsets
+
+
+def build_host_graph(w):
+    """The product's host-side graph for a host-built workload -> (SparseMatrix, input edge count E)."""
+    import cleora_b200 as cb
+    if w["kind"] == "hyper":
+        members, offsets = gen_hyperedges(w)
+        return cb.SparseMatrix.from_hyperedge_arrays(members, offsets, "complex::reflexive::product"), int(len(offsets) - 1)
+    u, v = gen_pairs(w)
+    return cb.SparseMatrix.from_edge_arrays(u, v), int(len(u))
+
+
+def build_oracle_graph(w):
+    """The CPU arms' graph, built by the oracle alone -> (OracleGraph, edge count, description of the sample)."""
+    import oracle
+    scale = w.get("cpu_sample", 1) if (w.get("device_gen") or w["kind"] == "hyper") else 1
+    if w["kind"] == "hyper":
+        members, offsets = gen_hyperedges(w, scale)
+        lines = [" ".join(map(str, members[offsets[i]:offsets[i + 1]])) for i in range(len(offsets) - 1)]
+        og, e = oracle.build_graph(lines, "complex::reflexive::product"), len(lines)
+    else:
+        u, v = gen_pairs_continuous(w, scale) if w.get("device_gen") else gen_pairs(w)
+        og, e = oracle.graph_from_pairs(u, v), len(u)
+    what = ("the full workload" if scale == 1 else
+            f"a 1/{scale}-scale graph of the same family ({og.n} nodes / {e} edges; edges/s is size-normalised)")
+    return og, int(e), what
+
+
+def gen_pairs_continuous(w, scale=1):
+    """Host restatement of the device generator's distribution for `device_gen` workloads (same family, not the same
+    stream): n / scale nodes, e / scale pairs, endpoint rank from the continuous inverse CDF of (x + 10)^-alpha, ids
+    decoupled from the rank by a random permutation.  Used by the CPU arms only."""
+    rs = np.random.default_rng(w["seed"])
+    n, e = max(2, w["n"] // scale), max(1, w["e"] // scale)
+    if w["kind"] == "er":
+        u, v = rs.integers(0, n, size=e, dtype=np.int64), rs.integers(0, n, size=e, dtype=np.int64)
+    else:
+        e1, i0 = 1.0 - w["alpha"], 10.0
+        a, b = i0 ** e1, (n + i0) ** e1
+        perm = rs.permutation(n)
+        draw = lambda: perm[np.minimum(((a + rs.random(e) * (b - a)) ** (1.0 / e1) - i0).astype(np.int64), n - 1)]  # noqa: E731
+        u, v = draw(), draw()
     keep = u != v
     return u[keep].astype(np.uint32), v[keep].astype(np.uint32)
 
@@ -142,24 +215,23 @@ def run_reference(args, w, name):
         return
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    u, v = gen_pairs(w)
-    og = oracle.graph_from_pairs(u, v)                  # host-only CSR construction, outside the timed region
+    og, n_edges, what = build_oracle_graph(w)           # host-only CSR construction, outside the timed region
     sample_iters = args.cpu_iters
     for _ in range(min(args.warmup, 1)):
         cpu_loop(og, w["d"], 1, args.whiten, cores)
     times = [cpu_loop(og, w["d"], sample_iters, args.whiten, cores) for _ in range(args.steps)]
     t = sum(times) / len(times)
-    value = len(u) * sample_iters / t
+    value = n_edges * sample_iters / t
     line = {
         "impl": "reference", "metric": "edges/sec through the 40-iteration embed() loop", "value": value,
         "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "nodes": og.n, "edges": int(len(u)), "nnz": og.nnz, "d": w["d"],
+        "config": {"workload": name, "nodes": og.n, "edges": n_edges, "nnz": og.nnz, "d": w["d"],
                    "iters": args.iters, "whiten": bool(args.whiten)},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_iters} of {args.iters} iterations of the full workload per step "
-                                   "(restated Rust/rayon SpMM+L2 in C/OpenMP + the reference's numpy whitening)"},
+                         "sample": f"{sample_iters} of {args.iters} iterations per step of {what}"
+                                   " (restated Rust/rayon SpMM+L2 in C/OpenMP + the reference's numpy whitening)"},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "product_library_loaded": any("libcleora_b200" in ln for ln in open("/proc/self/maps")),
     }
@@ -242,12 +314,18 @@ def run_ours(args, w, name):
     _lib.check(L.cleora_set_device(local))
     if world > 1:
         from cleora_b200 import sharded
-        return sharded.bench(args, w, name, gen_pairs, spmm_bytes, measured_peaks, ClockSampler)
+        return sharded.bench(args, w, name, build_host_graph, spmm_bytes, measured_peaks, ClockSampler)
 
     d, iters = w["d"], args.iters
-    u, v = gen_pairs(w)
-    g = cb.SparseMatrix.from_edge_arrays(u, v)
-    n, nnz, E = g.num_entities, g.num_edges, int(len(u))
+    device_gen = bool(w.get("device_gen"))
+    if device_gen:          # pair stream and CSR made on the device (see WORKLOADS); nothing of the graph on the host
+        u_d, v_d = cb.synth_pairs(w["kind"], w["n"], w["e"], w["seed"], w.get("alpha", 0.5))
+        g = cb.SparseMatrix.from_edge_arrays_device(u_d, v_d, want_sym=False)
+        E = int(w["e"])
+        u = v = None
+    else:
+        g, E = build_host_graph(w)
+    n, nnz = g.num_entities, g.num_edges
     norm = _lib.NORM_L2_NUMPY if args.whiten else _lib.NORM_L2_RUST
     dev_out = torch.empty((n, d), dtype=torch.float32, device="cuda")     # result stays in HBM for `value`
     timings = np.zeros(8)
@@ -289,22 +367,51 @@ def run_ours(args, w, name):
     ms_step = ev0.elapsed_time(ev1) / args.steps
     value = E * iters / (ms_step * 1e-3)
 
-    # ---- e2e: public host API, host buffers; every step copies the CSR host -> device again (same device buffers,
-    # pinned host arrays) and the result device -> pinned host memory inside the timed region.  X0 is produced on the
-    # device by the init kernel from the uploaded entity hashes (the reference also initialises inside embed()).
-    pinned = cb.pinned_empty((n, d), np.float32)
+    # ---- e2e: public host API on HOST buffers, host<->device copies inside the timed region.
     e2e_times = []
-    for i in range(1 + args.e2e_steps):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        _lib.check(L.cleora_graph_refresh_device(g._handle(), None))
-        g.embed_device(d, iters, "left", norm, 0, None, 0.0, 0.0, bool(args.whiten), out=pinned)
-        torch.cuda.synchronize()
-        if i > 0:
-            e2e_times.append(time.perf_counter() - t0)
+    if not device_gen:
+        # every step copies the CSR host -> device again (same device buffers, pinned host arrays) and the result
+        # device -> pinned host memory.  X0 is produced on the device by the init kernel from the uploaded entity
+        # hashes (the reference also initialises inside embed()).
+        pinned = cb.pinned_empty((n, d), np.float32)
+        for i in range(1 + args.e2e_steps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _lib.check(L.cleora_graph_refresh_device(g._handle(), None))
+            g.embed_device(d, iters, "left", norm, 0, None, 0.0, 0.0, bool(args.whiten), out=pinned)
+            torch.cuda.synchronize()
+            if i > 0:
+                e2e_times.append(time.perf_counter() - t0)
+        h2d = 8 * (n + 1) + nnz * (4 + 4) + 8 * n     # rowptr + col + left values + hashes (sym values only on first symmetric use)
+        e2e_note = ("cleora_b200 host API on host buffers: CSR re-copied host->device and result copied to pinned host "
+                    "memory every step; X0 comes from the init kernel (entity hashes are part of the upload)")
+    else:
+        # the edge list lives in pinned host memory; every step uploads it, builds the CSR on the device
+        # (from_edge_arrays_device), runs the loop and copies the result to pinned host memory
+        hu, hv = cb.pinned_empty((E,), np.int32), cb.pinned_empty((E,), np.int32)
+        torch.from_numpy(hu).copy_(u_d)
+        torch.from_numpy(hv).copy_(v_d)
+        del g, dev_out
+        L.cleora_release_workspace()
+        torch.cuda.empty_cache()
+        pinned = cb.pinned_empty((n, d), np.float32)
+        for i in range(1 + max(1, args.e2e_steps - 1)):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            u_d.copy_(torch.from_numpy(hu), non_blocking=True)
+            v_d.copy_(torch.from_numpy(hv), non_blocking=True)
+            g2 = cb.SparseMatrix.from_edge_arrays_device(u_d, v_d, want_sym=False)
+            g2.embed_device(d, iters, "left", norm, 0, None, 0.0, 0.0, bool(args.whiten), out=pinned)
+            torch.cuda.synchronize()
+            if i > 0:
+                e2e_times.append(time.perf_counter() - t0)
+            del g2
+        g = None
+        h2d = 8 * E
+        e2e_note = ("edge list (2 x uint32 per edge) in pinned host memory -> device, CSR built on the device "
+                    "(cleora_dev_graph_from_pairs), loop, result copied to pinned host memory -- all inside the timed region")
     eigh_ctx.__exit__(None, None, None)
     e2e_t = sum(e2e_times) / len(e2e_times)
-    h2d = 8 * (n + 1) + nnz * (4 + 4) + 8 * n     # rowptr + col + left values + hashes (sym values only on first symmetric use)
     d2h = 4 * n * d
 
     # ---- roofline of the dominant kernel (K1 SpMM+L2), live CUDA-event time from the same timed region
@@ -324,7 +431,9 @@ def run_ours(args, w, name):
 
     # ---- second stated baseline: the reference's own torch GPU path on this GPU (bounded sample)
     tbase = None
-    if args.torch_iters > 0:
+    if args.torch_iters > 0 and device_gen:
+        tbase = {"unavailable": "graph is device-resident only (no COO on the host); run a host-built workload"}
+    elif args.torch_iters > 0:
         try:
             L.cleora_release_workspace()
             torch.cuda.empty_cache()
@@ -342,18 +451,22 @@ def run_ours(args, w, name):
         import oracle
         cores = os.cpu_count() or 1
         os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-        og = oracle_graph_from(g)
+        if device_gen or w["kind"] == "hyper":
+            og, e_cpu, what = build_oracle_graph(w)
+        else:
+            og, e_cpu, what = oracle_graph_from(g), E, "the full workload"
         cpu_loop(og, d, 1, args.whiten, cores)
         tc = cpu_loop(og, d, args.cpu_iters, args.whiten, cores)
-        cpu = {"value": E * args.cpu_iters / tc, "unit": "edges/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_iters} of {iters} iterations of the full workload, restated Rust/rayon SpMM+L2 "
+        cpu = {"value": e_cpu * args.cpu_iters / tc, "unit": "edges/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_iters} of {iters} iterations of {what}, restated Rust/rayon SpMM+L2 "
                          "(C/OpenMP, oracle/) + the reference's numpy whitening"}
 
     chol = bool(L.cleora_get_option(b"chol_whiten")) and bool(args.whiten)
     line = {
         "metric": "edges/sec through the 40-iteration embed() loop", "value": value, "unit": "edges/s",
         "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic" + (" (generated and ingested on the device)" if device_gen else ""),
         "config": {"workload": name, "nodes": n, "edges": E, "nnz": nnz, "d": d, "iters": iters,
                    "whiten": bool(args.whiten),
                    "inner_whitening": ("Cholesky factor on the device (iterations 0..T-2), PCA eigh on the last" if chol
@@ -363,9 +476,7 @@ def run_ours(args, w, name):
                    "l2_flush": "inputs (X + CSR per iteration) exceed the 126 MB L2"},
         "nnz_per_s": nnz * iters / (ms_step * 1e-3),
         "e2e": {"value": E * iters / e2e_t, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_t, "samples": len(e2e_times), "ms_min": 1e3 * min(e2e_times),
-                "note": "cleora_b200 host API on host buffers: CSR re-copied host->device and result copied to pinned "
-                        "host memory every step; X0 comes from the init kernel (entity hashes are part of the upload)"},
+                "ms_per_step": 1e3 * e2e_t, "samples": len(e2e_times), "ms_min": 1e3 * min(e2e_times), "note": e2e_note},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel (K1: SpMM + fused L2)", "achieved": achieved,

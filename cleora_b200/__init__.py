@@ -77,8 +77,11 @@ def whiten_embeddings(embeddings: np.ndarray, n_components: Optional[int] = None
     n, d = x.shape
     if n <= 1:
         return embeddings.copy()
-    dout = d if n_components is None else min(int(n_components), d)
+    # `eigenvectors[:, :n_components]` (pycleora/__init__.py:151-153): slice semantics, including 0 and negatives
+    dout = d if n_components is None else len(range(d)[:int(n_components)])
     out = np.empty((n, dout), np.float32)
+    if dout == 0:
+        return out
     check(_lib.lib().cleora_whiten_embeddings(ptr(x, _lib.c_f32p), n, d, dout, ptr(out, _lib.c_f32p)))
     return out
 

@@ -36,6 +36,7 @@ PROTOTYPES = {
     "cleora_graph_from_lines": (C.c_int, [C.c_char_p, c_i64p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "cleora_graph_from_files": (C.c_int, [C.POINTER(C.c_char_p), C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "cleora_graph_from_pairs": (C.c_int, [c_u32p, c_u32p, C.c_int64, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "cleora_graph_from_hyperedges": (C.c_int, [c_u32p, c_i64p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "cleora_dev_graph_from_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_int, C.c_int, C.c_int,
                                               C.c_void_p, C.POINTER(C.c_void_p), c_i64p]),
     "cleora_dev_synth_pairs": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_void_p, C.c_void_p,
@@ -86,6 +87,13 @@ PROTOTYPES = {
                                        C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "cleora_dev_whiten_apply_push": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                                C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cleora_dev_spmm_scatter": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_int, C.c_int64,
+                                          C.c_int64, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
+    "cleora_dev_whiten_apply_slices": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                                 C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int, C.c_void_p,
+                                                 C.c_void_p]),
+    "cleora_dev_normalize_slices": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
+                                              C.c_int, C.c_int64, C.c_void_p]),
     "cleora_dev_malloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "cleora_dev_free": (C.c_int, [C.c_void_p]),
     "cleora_ipc_get_handle": (C.c_int, [C.c_void_p, C.c_char_p]),

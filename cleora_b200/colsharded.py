@@ -1,0 +1,359 @@
+"""Column-sharded multi-GPU embed loop: the SpMM runs on COLUMN slices of the iterate, the dense stages on ROW blocks,
+and the two transposes between the layouts are all-to-alls fused into the producing kernels' epilogues over NVLink
+peer memory.  One process per GPU (``torch.distributed`` for plumbing), every numerical step in the library's kernels.
+
+Why (measured in round 1): with rows sharded, every rank needs the WHOLE iterate before each SpMM -- an
+all-gather that delivers (G-1)/G * n*d*4 bytes to every GPU per iteration (2.2 GB at C3, 18.7 GB at C5), as long as the
+SpMM itself on 8 GPUs.  The SpMM is linear in the columns of X, so shard the columns instead:
+
+  layout B (SpMM):   rank g holds X[:, g*ds:(g+1)*ds] for ALL rows and the WHOLE CSR (1-24 GB; HBM has 180 GB).
+                     W[:, slice g] = A @ X[:, slice g] needs no communication at all; per-GPU traffic is nnz*(8 + 4*ds)
+                     bytes, ~1/G of the single-GPU SpMM, perfectly balanced (every rank walks every row).
+  layout A (dense):  rank h owns rows [h*block, (h+1)*block) with all d columns: row norms, column sums, covariance,
+                     the d x d transform and the apply GEMM are row-local; their couplings are the usual two small
+                     all-reduces (d and d*d doubles).
+
+Between them the matrix is transposed twice per iteration, n*d*4/G bytes per GPU each way (8x less than the gather):
+  B -> A   K1's epilogue stores row r of its slice straight into the owner's W buffer   (cleora_dev_spmm_scatter)
+  A -> B   K3's (or the row normaliser's) epilogue stores each column slice of its rows into the slice owner's X buffer
+           (cleora_dev_whiten_apply_slices / cleora_dev_normalize_slices), 64-512 contiguous bytes per store instruction.
+A tiny all-reduce after K1 and the covariance all-reduce after K3 are the only synchronisation points (each rank may
+overwrite a buffer only after every rank has finished reading it).
+
+Accumulation order inside a row is untouched and the row normalisation replays K1's summation tree, so the
+``whiten=False`` result is bit-identical to one GPU for every rank count.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .pycleora import SparseMatrix
+from .sharded import CudaBackend, _CudaArray, _DevPtr
+
+SPMM_WIDTHS = (8, 16, 32, 64, 96, 128, 192, 256, 384, 512, 1024)     # kernels.cu: launch_spmm / launch_normalize_rows
+
+
+def eligible(d: int, world: int) -> bool:
+    """Shapes the column-sharded loop covers: an even column split whose slice has a vectorised SpMM kernel."""
+    return (1 < world <= 8 and d % world == 0 and (d // world) in SPMM_WIDTHS and d in SPMM_WIDTHS
+            and os.environ.get("CLEORA_B200_COLSHARD", "1") != "0")
+
+
+class CudaPeerBuffer:
+    """A [rows, cols] f32 buffer on this GPU that every rank of the node can store into: ``tensor`` is the local view,
+    ``dests`` the addresses of all ranks' buffers in rank order (own one included) as mapped into this process."""
+
+    def __init__(self, be, rows, cols, dist, group, rank, world):
+        self.be, self.L = be, be.L
+        nbytes = max(rows * cols * 4, 4)
+        p = C.c_void_p()
+        check(self.L.cleora_dev_malloc(nbytes, C.byref(p)))
+        h = C.create_string_buffer(64)
+        check(self.L.cleora_ipc_get_handle(p, h))
+        self.ptr = p.value
+        everyone = [None] * world
+        dist.all_gather_object(everyone, h.raw, group=group)
+        self.dests, self._opened = [], []
+        for r in range(world):
+            if r == rank:
+                self.dests.append(self.ptr)
+            else:
+                q = C.c_void_p()
+                check(self.L.cleora_ipc_open(everyone[r], C.byref(q)))
+                self.dests.append(q.value)
+                self._opened.append(q.value)
+        self.tensor = be.torch.as_tensor(_CudaArray(self.ptr, (max(rows, 1), cols)), device=be.device)
+        self.tensor.zero_()
+
+    def close(self):
+        for q in self._opened:
+            self.L.cleora_ipc_close(q)
+        self._opened = []
+        if self.ptr:
+            self.L.cleora_dev_free(self.ptr)
+            self.ptr = None
+
+
+class ColumnBackend(CudaBackend):
+    """CudaBackend plus the three fused-transpose kernels and peer buffers."""
+
+    def peer_buffer(self, name, rows, cols, dist, group, rank, world):
+        return CudaPeerBuffer(self, rows, cols, dist, group, rank, world)
+
+    def _ptrs(self, dests):
+        return (C.c_void_p * len(dests))(*dests)
+
+    def spmm_scatter(self, graph, markov, x_slice, ds, wa, block, d, col_off, resid, alpha, rw):
+        check(self.L.cleora_dev_spmm_scatter(graph._handle(), markov, x_slice.data_ptr(), ds, self._ptrs(wa.dests), len(wa.dests),
+                                             block, d, col_off, None if resid is None else resid.data_ptr(), alpha, rw,
+                                             self.stream()))
+
+    def apply_slices(self, x, n, d, mean32, T, out, xb, row_base, norm, rowscale):
+        check(self.L.cleora_dev_whiten_apply_slices(x.data_ptr(), n, d, mean32.data_ptr(), T.data_ptr(), d, out.data_ptr(),
+                                                    self._ptrs(xb.dests), len(xb.dests), row_base, norm,
+                                                    None if rowscale is None else rowscale.data_ptr(), self.stream()))
+
+    def normalize_slices(self, x, n, d, norm, out, xb, row_base):
+        """K1's row normalisation of x[n, d] into `out`; with `xb` also every column slice into its owner's copy."""
+        dests = [] if xb is None else xb.dests
+        check(self.L.cleora_dev_normalize_slices(x.data_ptr(), n, d, norm, out.data_ptr(),
+                                                 self._ptrs(dests) if dests else None, len(dests), row_base, self.stream()))
+
+    def init_slice(self, hash_ptr, n, ds, seed, x):
+        check(self.L.cleora_dev_init(hash_ptr, n, ds, seed, x.data_ptr(), self.stream()))
+
+    def row_scale_full(self, graph, markov, out):
+        check(self.L.cleora_dev_row_scale(graph._handle(), markov, out.data_ptr(), self.stream()))
+
+    def graph_hashes(self, graph):
+        hp, nh = C.c_void_p(), C.c_int64()
+        check(self.L.cleora_dev_graph_hashes(graph._handle(), C.byref(hp), C.byref(nh)))
+        return hp.value, int(nh.value)
+
+    def spmm_graph(self, graph, markov, x, d, y, resid, alpha, rw, norm):
+        check(self.L.cleora_dev_spmm(graph._handle(), markov, x.data_ptr(), d, y.data_ptr(),
+                                     None if resid is None else resid.data_ptr(), alpha, rw, norm, self.stream()))
+
+    def tc_apply_ok(self, d):
+        return bool(self.L.cleora_whiten_apply_fusable(d, d))
+
+
+def _wrap64(v: int) -> int:
+    """seed + offset with the i64 wrap-around of the init hash (src/lib.rs:478-488), as a signed 64-bit value."""
+    v &= (1 << 64) - 1
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+class ColumnShardedEmbedder:
+    """Device-resident embed() (pycleora/__init__.py:51-127) over `world` GPUs, column-sharded SpMM (module docstring).
+    `graph` is the WHOLE graph on this rank's device (host-built SparseMatrix or a device-built one)."""
+
+    def __init__(self, graph: SparseMatrix, d: int, rank: int, world: int, backend=None, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.graph, self.d, self.rank, self.world = graph, d, rank, world
+        self.be = be = backend if backend is not None else ColumnBackend(torch.cuda.current_device())
+        self.n = n = graph.num_entities
+        self.ds = d // world
+        self.block = (n + world - 1) // world if n else 0
+        self.r0 = min(rank * self.block, n)
+        self.r1 = min(self.r0 + self.block, n)
+        self.n_local = self.r1 - self.r0
+        self.n_pad = self.block * world
+        f32, f64 = torch.float32, torch.float64
+        # peer-writable: the column slice of the iterate (all rows) and the W rows of the own block (all columns)
+        self.xb = be.peer_buffer("xb", max(self.n_pad, 1), self.ds, dist, group, rank, world)
+        self.wa = be.peer_buffer("wa", max(self.block, 1), d, dist, group, rank, world)
+        self.ya = be.empty((max(self.block, 1), d), f32)        # own rows, normalised (statistics are taken from these)
+        self.ya2 = be.empty((max(self.block, 1), d), f32)
+        self.prev = None
+        self.sums, self.cov = be.empty((d,), f64), be.empty((d, d), f64)
+        self.mean32, self.T = be.empty((d,), f32), be.empty((d, d), f32)
+        self.scalar = be.empty((1,), f64)
+        self.status = be.empty((1,), torch.int32)
+        self.flag = be.empty((1,), f32)
+        self.rowscale = be.empty((max(n, 1),), f32)
+        self._rowscale_markov = None
+        for t in (self.ya, self.ya2, self.status, self.flag):
+            t.zero_()
+        self.hash_ptr, _ = be.graph_hashes(graph)
+        self._streams = None
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _barrier(self, group=None):
+        """Every rank has finished the kernels it enqueued before this point (tiny all-reduce on the current stream)."""
+        self.dist.all_reduce(self.flag, group=group if group is not None else self.group)
+
+    def _own(self, t):
+        return t[:max(self.n_local, 0)]
+
+    def _init(self, seed, x0):
+        be, n = self.be, self.n
+        if x0 is not None:
+            x0 = np.ascontiguousarray(x0, np.float32)
+            sl = np.zeros((max(self.n_pad, 1), self.ds), np.float32)
+            sl[:n] = x0[:, self.rank * self.ds:(self.rank + 1) * self.ds]
+            self.xb.tensor.copy_(be.from_numpy(sl))
+        elif n:
+            be.init_slice(self.hash_ptr, n, self.ds, _wrap64(seed + self.rank * self.ds), self.xb.tensor)
+
+    def _spmm(self, markov, resid, alpha, rw, timers=None):
+        """W rows of every rank's block <- A @ X[:, own slice] (+ residual), scattered to the owners; then all ranks sync."""
+        t = timers.start("spmm") if timers else None
+        self.be.spmm_scatter(self.graph, markov, self.xb.tensor, self.ds, self.wa, max(self.block, 1), self.d,
+                             self.rank * self.ds, self.xb.tensor if resid else None, alpha, rw)
+        if timers:
+            timers.stop(t)
+        t = timers.start("gather") if timers else None
+        self._barrier()
+        if timers:
+            timers.stop(t)
+
+    def _stats(self, y, timers=None):
+        be, dist, n = self.be, self.dist, self.n
+        t = timers.start("stats") if timers else None
+        be.col_sums(y, self.n_local, self.d, self.sums)
+        dist.all_reduce(self.sums, group=self.group)
+        self.sums.div_(float(n))
+        be.gram(y, self.n_local, self.d, self.sums, self.cov)
+        dist.all_reduce(self.cov, group=self.group)            # also the barrier after the slice stores of this iteration
+        self.cov.mul_(1.0 / float(n - 1))
+        self.mean32.copy_(self.sums)
+        if timers:
+            timers.stop(t)
+
+    def _pca_transform(self):
+        if self.rank == 0:
+            self.be.transform(self.cov, self.d, self.T)
+        self.dist.broadcast(self.T, src=0, group=self.group)
+
+    def _status_ok(self) -> bool:
+        flag = self.status.clone()
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX, group=self.group)
+        return int(flag.item()) == 0
+
+    # ------------------------------------------------------------------------------------------ loops
+    def run(self, iters, markov=0, norm=_lib.NORM_L2_NUMPY, seed=0, x0=None, residual_weight=0.0,
+            convergence_threshold=0.0, whiten=True, rust_semantics=False, timers=None, _allow_chol=True) -> int:
+        """Reference stage order (any configuration).  The final iterate's own rows are left in self.result_rows."""
+        torch, be, d, n = self.torch, self.be, self.d, self.n
+        if rust_semantics:                                   # src/embedding.rs:116
+            use_res = 0.0 < residual_weight < 1.0
+            alpha, rw = float(np.float32(1.0) - np.float32(residual_weight)), float(np.float32(residual_weight))
+        else:                                                # pycleora/__init__.py:114
+            use_res = residual_weight > 0
+            alpha, rw = float(np.float32(1.0 - residual_weight)), float(np.float32(residual_weight))
+        conv = convergence_threshold > 0
+        do_whiten = whiten and n > 1
+        inner_chol = (_allow_chol and do_whiten and not conv and iters >= 2 and be.chol_enabled(d)
+                      and norm in (_lib.NORM_L2_NUMPY, _lib.NORM_NONE))
+        if inner_chol:
+            self.status.zero_()
+        self._init(seed, x0)
+        if conv and self.prev is None:
+            self.prev = be.empty(tuple(self.ya.shape), torch.float32)
+        cur, other = self.ya, self.ya2
+        have_prev = False
+        done = 0
+        for it in range(iters):
+            self._spmm(markov, use_res, alpha, rw, timers)
+            if do_whiten:
+                be.normalize_slices(self.wa.tensor, self.n_local, d, norm, other, None, self.r0)      # local rows only
+                self._stats(other, timers)
+                t = timers.start("eigh") if timers else None
+                if inner_chol and it + 1 < iters:
+                    be.chol(self.cov, d, self.T, self.status)
+                else:
+                    self._pca_transform()
+                if timers:
+                    timers.stop(t)
+                t = timers.start("apply") if timers else None
+                be.apply(other, self.n_local, d, self.mean32, self.T, cur)
+                be.normalize_slices(cur, self.n_local, d, _lib.NORM_NONE, other, self.xb, self.r0)   # A -> B copy of the new iterate
+                if timers:
+                    timers.stop(t)
+                fresh = cur
+            else:
+                be.normalize_slices(self.wa.tensor, self.n_local, d, norm, other, self.xb, self.r0)
+                fresh = other
+            self._barrier()
+            done = it + 1
+            stop = False
+            if conv and have_prev:
+                be.sq_diff(fresh, self.prev, self.n_local * d, not rust_semantics, self.scalar)
+                self.dist.all_reduce(self.scalar, group=self.group)
+                tot = float(self.scalar.item())
+                rmse = float(np.sqrt(np.float32(tot) / np.float32(n * d))) if rust_semantics else float(np.sqrt(tot / (n * d)))
+                stop = rmse < convergence_threshold
+            if conv:
+                self.prev.copy_(fresh)
+                have_prev = True
+            self.result_rows = fresh
+            if fresh is other:
+                cur, other = other, cur
+            if stop:
+                break
+        if inner_chol and not self._status_ok():
+            return self.run(iters, markov, norm, seed, x0, residual_weight, convergence_threshold, whiten, rust_semantics,
+                            timers, _allow_chol=False)
+        return done
+
+    def pipeline_eligible(self, iters, norm, residual_weight, convergence_threshold, whiten) -> bool:
+        return (bool(whiten) and self.n > 1 and iters >= 2 and norm == _lib.NORM_L2_NUMPY and residual_weight == 0
+                and convergence_threshold <= 0 and self.be.tc_apply_ok(self.d)
+                and os.environ.get("CLEORA_B200_PIPELINE", "1") != "0")
+
+    def run_pipelined(self, iters, markov=0, seed=0, x0=None, timers=None, _allow_chol=True) -> int:
+        """Default configuration.  Per iteration: W = A Y on column slices (K1, scattered to the row owners) while the
+        transform of Y is factorised on a side stream; X' = rownorm((W - s mu^T) T) on the tensor cores with the column
+        slices of the result stored straight into their owners' copies; statistics of the new rows.  Same algebra as
+        the single-GPU pipelined loop (abi.cu: embed_pipelined)."""
+        be, d, n, dist = self.be, self.d, self.n, self.dist
+        if self._streams is None:
+            self._streams = (be.new_stream(), dist.new_group())
+        side, g_bcast = self._streams
+        main = be.current()
+        inner_chol = _allow_chol and be.chol_enabled(d)
+        if inner_chol:
+            self.status.zero_()
+        if self._rowscale_markov != markov:
+            be.row_scale_full(self.graph, markov, self.rowscale)
+            self._rowscale_markov = markov
+        rs_own = self.rowscale[self.r0:self.r0 + max(self.n_local, 1)]
+        self._init(seed, x0)
+        y, y2 = self.ya, self.ya2
+        # iteration 0: Y = rownorm(A X0)
+        self._spmm(markov, False, 1.0, 0.0, timers)
+        t = timers.start("apply") if timers else None
+        be.normalize_slices(self.wa.tensor, self.n_local, d, _lib.NORM_L2_NUMPY, y, self.xb, self.r0)
+        if timers:
+            timers.stop(t)
+        self._stats(y, timers)
+        for it in range(1, iters):
+            side.wait_stream(main)                                   # covariance of this iterate is ready
+            with be.on(side):
+                t = timers.start("eigh") if timers else None
+                if inner_chol:
+                    be.chol(self.cov, d, self.T, self.status)        # every rank, identical input -> identical T
+                else:
+                    if self.rank == 0:
+                        be.transform(self.cov, d, self.T)
+                    dist.broadcast(self.T, src=0, group=g_bcast)
+                if timers:
+                    timers.stop(t)
+            self._spmm(markov, False, 1.0, 0.0, timers)               # W = A Y (needs no T)
+            main.wait_stream(side)
+            t = timers.start("apply") if timers else None
+            be.apply_slices(self.wa.tensor, self.n_local, d, self.mean32, self.T, y2, self.xb, self.r0, _lib.NORM_L2_NUMPY, rs_own)
+            if timers:
+                timers.stop(t)
+            self._stats(y2, timers)                                   # its all-reduce: every rank's slices have landed
+            y, y2 = y2, y
+        # the iterate that leaves the loop: PCA transform of the last Y (reference semantics)
+        self._pca_transform()
+        be.apply(y, self.n_local, d, self.mean32, self.T, y2)
+        self.result_rows = y2
+        if inner_chol and not self._status_ok():
+            return self.run_pipelined(iters, markov, seed, x0, timers, _allow_chol=False)
+        return iters
+
+    def result(self) -> np.ndarray:
+        """The full final iterate on every rank (all-gather of the row blocks)."""
+        torch = self.torch
+        full = self.be.empty((max(self.n_pad, 1), self.d), torch.float32)
+        blk = self.be.empty((max(self.block, 1), self.d), torch.float32)
+        blk.zero_()
+        blk[:self.n_local].copy_(self.result_rows[:self.n_local])
+        self.dist.all_gather_into_tensor(full, blk, group=self.group)
+        return full[:self.n].cpu().numpy()
+
+    def close(self):
+        self.xb.close()
+        self.wa.close()

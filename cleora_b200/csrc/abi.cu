@@ -732,6 +732,16 @@ extern "C" int cleora_graph_from_pairs(const uint32_t *u, const uint32_t *v, int
         *out = static_cast<cleora_graph_t *>(g.release());
     });
 }
+extern "C" int cleora_graph_from_hyperedges(const uint32_t *members, const int64_t *offsets, int64_t n_lines,
+                                            const char *columns, int64_t trim_n, cleora_graph_t **out) {
+    return guarded([&] {
+        if (n_lines < 0 || !offsets || (n_lines && offsets[0] != 0)) value_error("bad hyperedge offsets");
+        for (int64_t i = 0; i < n_lines; ++i)
+            if (offsets[i + 1] < offsets[i]) value_error("hyperedge offsets must be non-decreasing");
+        auto g = build_from_hyperedges(members, offsets, n_lines, columns, trim_n);
+        *out = static_cast<cleora_graph_t *>(g.release());
+    });
+}
 extern "C" int cleora_dev_graph_from_pairs(const uint32_t *u, const uint32_t *v, int64_t n_pairs, const char *column_name,
                                            int shard_rank, int shard_world, int want_sym, void *stream,
                                            cleora_graph_t **out, int64_t *bounds_out) {
@@ -933,9 +943,60 @@ extern "C" int cleora_dev_whiten_apply_push(const float *x, int64_t n, int64_t d
                                             int64_t dout, float *out, float *const *extra_outs, int n_extra,
                                             int normalization, const float *rowscale, void *stream) {
     return guarded([&] {
-        if (!whiten_apply_tc_supported(d, dout)) value_error("fused apply needs d % 32 == 0, dout % 16 == 0, dout <= 256");
+        if (!whiten_apply_tc_supported(d, dout)) value_error("fused apply needs d % 32 == 0 and dout % 32 == 0, dout <= 256 (or dout % 64 == 0, dout <= 512)");
         const PeerOut peers = make_peers(extra_outs, n_extra);
         launch_whiten_apply_tc(x, n, d, mean_f32, T, dout, out, normalization, rowscale, (cudaStream_t)stream, &peers);
+    });
+}
+// ---- column-sharded multi-GPU loop: the two all-to-alls are fused into the producers' epilogues ------------------
+static PeerOut make_dests(float *const *dests, int n_dst, int mode) {
+    if (n_dst < 1 || n_dst > 8) value_error("1 to 8 destinations");
+    PeerOut p{};
+    p.n_extra = n_dst;
+    p.mode = mode;
+    for (int i = 0; i < n_dst; ++i) {
+        if (!dests[i]) value_error("null destination");
+        p.extra[i] = dests[i];
+    }
+    return p;
+}
+extern "C" int cleora_dev_spmm_scatter(cleora_graph_t *g, int markov, const float *x, int64_t d, float *const *dests,
+                                       int n_dst, int64_t block_rows, int64_t ld_cols, int64_t col_off, const float *resid,
+                                       float alpha, float rw, void *stream) {
+    return guarded([&] {
+        DeviceGraph &dg = device_graph(*g);
+        if (block_rows <= 0 || (dg.n_rows + block_rows - 1) / block_rows > n_dst) value_error("row blocks do not cover the graph");
+        if (col_off < 0 || col_off % 4 != 0 || ld_cols % 4 != 0 || col_off + d > ld_cols) value_error("bad destination columns");
+        PeerOut peers = make_dests(dests, n_dst, PEER_OWNERS);
+        peers.block_rows = block_rows; peers.ld_cols = ld_cols; peers.col_off = (int)col_off;
+        launch_spmm(dg, values_of(dg, markov), x, d, nullptr, resid, alpha, rw, CLEORA_NORM_NONE, (cudaStream_t)stream, &peers);
+    });
+}
+extern "C" int cleora_dev_whiten_apply_slices(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
+                                              int64_t dout, float *out, float *const *dests, int n_dst, int64_t row_base,
+                                              int normalization, const float *rowscale, void *stream) {
+    return guarded([&] {
+        if (!whiten_apply_tc_supported(d, dout)) value_error("fused apply needs the tensor-core shape rules (see cleora_whiten_apply_fusable)");
+        if (dout % n_dst != 0 || (dout / n_dst) % 4 != 0) value_error("column slices must be multiples of 4 columns");
+        PeerOut peers = make_dests(dests, n_dst, PEER_SLICES);
+        peers.slice_cols = (int)(dout / n_dst); peers.row_base = row_base;
+        launch_whiten_apply_tc(x, n, d, mean_f32, T, dout, out, normalization, rowscale, (cudaStream_t)stream, &peers);
+    });
+}
+extern "C" int cleora_dev_normalize_slices(const float *x, int64_t n, int64_t d, int normalization, float *out,
+                                           float *const *dests, int n_dst, int64_t row_base, void *stream) {
+    return guarded([&] {
+        check_norm(normalization);
+        if (!normalize_rows_supported(d)) value_error("feature dimension has no vectorised row mapping");
+        if (!out) value_error("the local copy is required");
+        if (n_dst == 0) {                                           // local rows only
+            launch_normalize_rows(x, n, d, normalization, out, (cudaStream_t)stream, nullptr);
+            return;
+        }
+        if (d % n_dst != 0 || (d / n_dst) % 4 != 0) value_error("column slices must be multiples of 4 columns");
+        PeerOut peers = make_dests(dests, n_dst, PEER_SLICES);
+        peers.slice_cols = (int)(d / n_dst); peers.row_base = row_base;
+        launch_normalize_rows(x, n, d, normalization, out, (cudaStream_t)stream, &peers);
     });
 }
 // ---- peer memory plumbing (CUDA IPC): buffers that other ranks' kernels write into ------------------------------
@@ -981,7 +1042,7 @@ extern "C" int cleora_dev_whiten_apply_ex(const float *x, int64_t n, int64_t d, 
             launch_whiten_apply(x, n, d, mean_f32, T, dout, out, (cudaStream_t)stream);
             return;
         }
-        if (!whiten_apply_tc_supported(d, dout)) value_error("fused apply needs d % 32 == 0, dout % 16 == 0, dout <= 256");
+        if (!whiten_apply_tc_supported(d, dout)) value_error("fused apply needs d % 32 == 0 and dout % 32 == 0, dout <= 256 (or dout % 64 == 0, dout <= 512)");
         launch_whiten_apply_tc(x, n, d, mean_f32, T, dout, out, normalization, rowscale, (cudaStream_t)stream);
     });
 }
@@ -1112,8 +1173,8 @@ extern "C" int cleora_embed_fast_convergence(cleora_graph_t *g, int64_t d, int64
 extern "C" int cleora_whiten_embeddings(const float *x, int64_t n, int64_t d, int64_t n_components, float *out) {
     return guarded([&] {
         require_device();
-        const int64_t dout = n_components > 0 ? n_components : d;
-        if (dout > d) value_error("n_components must be <= feature dimension");
+        if (n_components <= 0 || n_components > d) value_error("n_components must be in [1, feature dimension]");
+        const int64_t dout = n_components;
         if (n <= 1) {                                            // pycleora/__init__.py:132-133
             if (n == 1) std::memcpy(out, x, sizeof(float) * (size_t)d);
             return;

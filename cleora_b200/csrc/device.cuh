@@ -37,12 +37,25 @@ struct DeviceGraph {
     std::mutex lazy_mu;                    // guards the lazily built members (sym, rsum_*)
 };
 
-// Extra destinations of a row-producing kernel: the same rows are also stored at these base pointers (peer GPUs'
-// copies of the gathered matrix, mapped through CUDA IPC) -- the all-gather fused into the producer's epilogue.
+// Where a row-producing kernel (K1, K3, the row normaliser) stores its rows besides / instead of `out`.  The pointers
+// may be other GPUs' buffers mapped through CUDA IPC (peer stores over NVLink): the collective is fused into the
+// producer's epilogue.
+//   mode 0  REPLICATE  the same full row also goes to extra[0 .. n_extra)            (all-gather of row blocks)
+//   mode 1  SLICES     columns [h*slice_cols, (h+1)*slice_cols) of row r go to extra[h] at row (row_base + r) of an
+//                      [rows x slice_cols] matrix, h = 0 .. n_extra-1                 (row-sharded -> column-sharded)
+//   mode 2  OWNERS     the produced rows have `ld_cols`-wide destinations: row r goes to extra[r / block_rows] at row
+//                      (r % block_rows), columns [col_off, col_off + d); `out` is unused (column-sharded -> row-sharded)
 struct PeerOut {
-    float *extra[7];
+    float *extra[8];
     int n_extra;
+    int mode;
+    int slice_cols;
+    int col_off;
+    int64_t row_base;
+    int64_t block_rows;
+    int64_t ld_cols;
 };
+enum { PEER_REPLICATE = 0, PEER_SLICES = 1, PEER_OWNERS = 2 };
 
 void set_error(const std::string &msg);
 extern std::atomic<int64_t> g_launches;
@@ -91,6 +104,9 @@ void launch_init(const uint64_t *hash, int64_t n, int64_t d, int64_t seed, float
 void launch_spmm(const DeviceGraph &g, const float *val, const float *x, int64_t d, float *out, const float *resid,
                  float alpha, float rw, int norm, cudaStream_t st, const PeerOut *peers = nullptr);
 void launch_normalize(const float *x, int64_t n, int64_t d, int norm, float *out, cudaStream_t st);
+// K1's fused row norm applied to existing rows, with K1's destinations (kernels.cu: normalize_rows_kernel)
+bool normalize_rows_supported(int64_t d);
+void launch_normalize_rows(const float *x, int64_t n, int64_t d, int norm, float *out, cudaStream_t st, const PeerOut *peers);
 // Per-block maxima of |x| (device), a by-product of the column-sum pass that the integer Gram kernel needs for its
 // fixed-point scale; count == 0 means "not produced" (the Gram launcher then makes its own pass).
 struct AbsmaxPartials {

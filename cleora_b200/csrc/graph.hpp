@@ -58,6 +58,8 @@ uint64_t xxh64(const void *data, size_t len, uint64_t seed);
 // from_iterator / from_files semantics; throw BuildError for the reference's ValueError cases.
 std::unique_ptr<Graph> build_from_lines(const char *buf, const int64_t *offsets, int64_t n_lines,
                                         const std::string &columns, int64_t trim_n);
+std::unique_ptr<Graph> build_from_hyperedges(const uint32_t *members, const int64_t *offsets, int64_t n_lines,
+                                             const std::string &columns, int64_t trim_n);
 std::unique_ptr<Graph> build_from_files(const std::vector<std::string> &paths, const std::string &columns,
                                         int64_t trim_n);
 std::unique_ptr<Graph> build_from_pairs(const uint32_t *u, const uint32_t *v, int64_t n_pairs,

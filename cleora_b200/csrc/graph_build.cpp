@@ -363,6 +363,29 @@ std::unique_ptr<Graph> build_from_lines(const char *buf, const int64_t *offsets,
     return b.finish();
 }
 
+// Integer hyperedges: line i = members[offsets[i] .. offsets[i+1]) as decimal ids of ONE column, i.e. exactly the
+// graph build_from_lines makes of the space-joined decimal strings -- the text of each line is formatted here and fed
+// through the same Builder (same hashing, indexing, trimming and accumulation order), only the Python-side string
+// handling is skipped.
+std::unique_ptr<Graph> build_from_hyperedges(const uint32_t *members, const int64_t *offsets, int64_t n_lines,
+                                             const std::string &columns, int64_t trim_n) {
+    Builder b(columns, trim_n);
+    std::string text;
+    char dec[12];
+    for (int64_t i = 0; i < n_lines; ++i) {
+        text.clear();
+        for (int64_t k = offsets[i]; k < offsets[i + 1]; ++k) {
+            if (k > offsets[i]) text.push_back(' ');
+            uint32_t x = members[k];
+            int len = 0;
+            do { dec[len++] = char('0' + x % 10); x /= 10; } while (x);
+            while (len) text.push_back(dec[--len]);
+        }
+        b.add_line(text.data(), 0, (int64_t)text.size());
+    }
+    return b.finish();
+}
+
 std::unique_ptr<Graph> build_from_files(const std::vector<std::string> &paths, const std::string &columns,
                                         int64_t trim_n) {
     Builder b(columns, trim_n);

@@ -152,9 +152,32 @@ __device__ __forceinline__ void finish_row(float4 (&acc)[VEC], int64_t row, bool
         }
     }
     if (valid) {
+        if (peers.mode == PEER_OWNERS) {                      // column-sharded SpMM: the row belongs to another rank's block
+            const int64_t owner = row / peers.block_rows, local = row - owner * peers.block_rows;
+            float4 *pp = nullptr;
+#pragma unroll
+            for (int p = 0; p < 8; ++p)                       // static indices keep the pointers in the constant bank
+                if (p == owner) pp = reinterpret_cast<float4 *>(peers.extra[p] + local * peers.ld_cols + peers.col_off) + gl;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) pp[v * LPR] = acc[v];
+            return;
+        }
         float4 *op = reinterpret_cast<float4 *>(out) + row * D4 + gl;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) op[v * LPR] = acc[v];
+        if (peers.mode == PEER_SLICES) {                      // row-sharded -> column-sharded: every float4 to its slice owner
+            const int sc4 = peers.slice_cols >> 2;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const int q = gl + v * LPR, owner = q / sc4;
+                float4 *pp = nullptr;
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+                    if (p == owner) pp = reinterpret_cast<float4 *>(peers.extra[p]) + (peers.row_base + row) * sc4 + (q - owner * sc4);
+                *pp = acc[v];
+            }
+            return;
+        }
 #pragma unroll
         for (int p = 0; p < 7; ++p) {                         // fused all-gather: the same row into the peers' copies
             if (p < peers.n_extra) {                          // (static indices keep the pointers in the constant bank)
@@ -166,7 +189,7 @@ __device__ __forceinline__ void finish_row(float4 (&acc)[VEC], int64_t row, bool
     }
 }
 
-// Rows with more than `long_threshold` edges are left to the long-row kernels below (only ever set for LPR == 32).
+// Rows with more than `long_threshold` edges are left to the long-row kernels below.
 template <int LPR, int VEC, int U>
 __global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restrict__ rowptr,
                                                         const uint32_t *__restrict__ col,
@@ -182,7 +205,11 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restric
     bool valid = row < n_rows;
     int64_t s = 0, e = 0;
     if (valid) { s = rowptr[row]; e = rowptr[row + 1]; }
-    if (LPR == 32 && e - s > long_threshold) return;            // warp-uniform: one row per warp
+    if (e - s > long_threshold) {                               // a hub row: the chunked kernels own it
+        if (LPR == 32) return;                                  // warp-uniform: one row per warp
+        e = s;
+        valid = false;
+    }
     float4 acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -190,10 +217,10 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restric
     finish_row<LPR, VEC>(acc, row, valid, gl, out, resid, alpha, rw, norm, peers);
 }
 
-// Long rows (hubs of power-law graphs): one warp per CHUNK of a long row writes a partial sum; one warp per long row
-// then adds the partials in chunk order and runs the usual epilogue.  Deterministic; the summation tree differs from
-// the sequential reference order for these rows only (documented deviation, a few ulp).
-template <int VEC, int U>
+// Long rows (hubs of power-law graphs): one lane group per CHUNK of a long row writes a partial sum; one lane group per
+// long row then adds the partials in chunk order and runs the usual epilogue.  Deterministic; the summation tree differs
+// from the sequential reference order for these rows only (documented deviation, a few ulp).
+template <int LPR, int VEC, int U>
 __global__ void __launch_bounds__(256) spmm_long_partial_kernel(const int64_t *__restrict__ rowptr,
                                                                 const uint32_t *__restrict__ col,
                                                                 const float *__restrict__ val,
@@ -202,44 +229,52 @@ __global__ void __launch_bounds__(256) spmm_long_partial_kernel(const int64_t *_
                                                                 const int64_t *__restrict__ chunk_ptr,
                                                                 const int32_t *__restrict__ chunk_owner, int64_t n_chunks,
                                                                 int64_t chunk_edges, float *__restrict__ partial) {
-    const int lane = threadIdx.x & 31;
-    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= n_chunks) return;
-    const int32_t ri = chunk_owner[c];
-    const int64_t row = long_rows[ri];
-    const int64_t s = rowptr[row] + (c - chunk_ptr[ri]) * chunk_edges;
-    const int64_t e = min(rowptr[row + 1], s + chunk_edges);
+    constexpr int RPW = 32 / LPR, D4 = LPR * VEC;
+    const int lane = threadIdx.x & 31, gl = lane & (LPR - 1);
+    const int64_t c = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+    const bool valid = c < n_chunks;
+    int64_t s = 0, e = 0;
+    if (valid) {
+        const int32_t ri = chunk_owner[c];
+        const int64_t row = long_rows[ri];
+        s = rowptr[row] + (c - chunk_ptr[ri]) * chunk_edges;
+        e = min(rowptr[row + 1], s + chunk_edges);
+    }
     float4 acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    accumulate_edges<32, VEC, U>(col, val, reinterpret_cast<const float4 *>(x), s, e, lane, acc);
-    float4 *pp = reinterpret_cast<float4 *>(partial) + c * (32 * VEC) + lane;
+    accumulate_edges<LPR, VEC, U>(col, val, reinterpret_cast<const float4 *>(x), s, e, gl, acc);
+    if (valid) {
+        float4 *pp = reinterpret_cast<float4 *>(partial) + c * D4 + gl;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) pp[v * 32] = acc[v];
+        for (int v = 0; v < VEC; ++v) pp[v * LPR] = acc[v];
+    }
 }
 
-template <int VEC>
+template <int LPR, int VEC>
 __global__ void __launch_bounds__(256) spmm_long_finish_kernel(const int64_t *__restrict__ long_rows,
                                                                const int64_t *__restrict__ chunk_ptr, int64_t n_long,
                                                                const float *__restrict__ partial, float *__restrict__ out,
                                                                const float *__restrict__ resid, float alpha, float rw,
                                                                int norm, PeerOut peers) {
-    const int lane = threadIdx.x & 31;
-    const int64_t ri = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (ri >= n_long) return;
+    constexpr int RPW = 32 / LPR, D4 = LPR * VEC;
+    const int lane = threadIdx.x & 31, gl = lane & (LPR - 1);
+    const int64_t ri = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+    const bool valid = ri < n_long;
     float4 acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t c = chunk_ptr[ri]; c < chunk_ptr[ri + 1]; ++c) {
-        const float4 *pp = reinterpret_cast<const float4 *>(partial) + c * (32 * VEC) + lane;
+    if (valid)
+        for (int64_t c = chunk_ptr[ri]; c < chunk_ptr[ri + 1]; ++c) {
+            const float4 *pp = reinterpret_cast<const float4 *>(partial) + c * D4 + gl;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const float4 p = pp[v * 32];
-            acc[v].x = __fadd_rn(acc[v].x, p.x); acc[v].y = __fadd_rn(acc[v].y, p.y);
-            acc[v].z = __fadd_rn(acc[v].z, p.z); acc[v].w = __fadd_rn(acc[v].w, p.w);
+            for (int v = 0; v < VEC; ++v) {
+                const float4 p = pp[v * LPR];
+                acc[v].x = __fadd_rn(acc[v].x, p.x); acc[v].y = __fadd_rn(acc[v].y, p.y);
+                acc[v].z = __fadd_rn(acc[v].z, p.z); acc[v].w = __fadd_rn(acc[v].w, p.w);
+            }
         }
-    }
-    finish_row<32, VEC>(acc, long_rows[ri], true, lane, out, resid, alpha, rw, norm, peers);
+    finish_row<LPR, VEC>(acc, valid ? long_rows[ri] : 0, valid, gl, out, resid, alpha, rw, norm, peers);
 }
 
 // Any d: one warp per row, lane owns columns lane, lane+32, ... in passes of T*32 columns.  Same accumulation
@@ -302,21 +337,19 @@ static void launch_rows(const DeviceGraph &g, const float *val, const float *x, 
     const int threads = 256;
     const int64_t rows_per_block = (int64_t)(threads / 32) * RPW;
     const int64_t blocks = (g.n_rows + rows_per_block - 1) / rows_per_block;
-    const bool split = LPR == 32 && g.n_long > 0;
+    const bool split = g.n_long > 0;
     spmm_rows_kernel<LPR, VEC, U><<<(unsigned)blocks, threads, 0, st>>>(
         g.rowptr, g.col, val, x, out, resid, g.n_rows, alpha, rw, norm, split ? g.long_threshold : INT64_MAX, peers);
     LAUNCH_CHECK();
-    if constexpr (LPR == 32) {
-        if (split) {
-            float *partial = (float *)workspace().spmm_partials.get((size_t)g.n_long_chunks * 128 * VEC * sizeof(float));
-            spmm_long_partial_kernel<VEC, U><<<(unsigned)((g.n_long_chunks + 7) / 8), threads, 0, st>>>(
-                g.rowptr, g.col, val, x, g.long_rows, g.long_chunk_ptr, g.long_chunk_owner, g.n_long_chunks,
-                g.long_chunk_edges, partial);
-            LAUNCH_CHECK();
-            spmm_long_finish_kernel<VEC><<<(unsigned)((g.n_long + 7) / 8), threads, 0, st>>>(
-                g.long_rows, g.long_chunk_ptr, g.n_long, partial, out, resid, alpha, rw, norm, peers);
-            LAUNCH_CHECK();
-        }
+    if (split) {
+        float *partial = (float *)workspace().spmm_partials.get((size_t)g.n_long_chunks * LPR * VEC * 4 * sizeof(float));
+        spmm_long_partial_kernel<LPR, VEC, U><<<(unsigned)((g.n_long_chunks + rows_per_block - 1) / rows_per_block), threads, 0, st>>>(
+            g.rowptr, g.col, val, x, g.long_rows, g.long_chunk_ptr, g.long_chunk_owner, g.n_long_chunks,
+            g.long_chunk_edges, partial);
+        LAUNCH_CHECK();
+        spmm_long_finish_kernel<LPR, VEC><<<(unsigned)((g.n_long + rows_per_block - 1) / rows_per_block), threads, 0, st>>>(
+            g.long_rows, g.long_chunk_ptr, g.n_long, partial, out, resid, alpha, rw, norm, peers);
+        LAUNCH_CHECK();
     }
 }
 
@@ -326,6 +359,7 @@ void launch_spmm(const DeviceGraph &g, const float *val, const float *x, int64_t
     PeerOut peers{};
     if (peers_in) peers = *peers_in;
     if (g.n_rows > (int64_t)0x7fffffff * 8) throw CudaFail{"too many rows for one launch"};
+    if (peers.mode == PEER_OWNERS && norm != CLEORA_NORM_NONE) throw CudaFail{"row scatter produces column slices: no fused row norm"};
     switch (d) {
         case 8:    launch_rows<2, 1, 2>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
         case 16:   launch_rows<4, 1, 4>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
@@ -340,7 +374,7 @@ void launch_spmm(const DeviceGraph &g, const float *val, const float *x, int64_t
         case 1024: launch_rows<32, 8, 2>(g, val, x, out, resid, alpha, rw, norm, st, peers); return;
         default: break;
     }
-    if (peers.n_extra) throw CudaFail{"peer push needs a vectorised feature dimension (8..1024 as listed)"};
+    if (peers.n_extra || peers.mode != PEER_REPLICATE) throw CudaFail{"peer push needs a vectorised feature dimension (8..1024 as listed)"};
     const int threads = 256;
     const int64_t blocks = (g.n_rows + 7) / 8;
     spmm_generic_kernel<8><<<(unsigned)blocks, threads, 0, st>>>(g.rowptr, g.col, val, x, out, resid, g.n_rows,
@@ -366,6 +400,57 @@ __global__ void __launch_bounds__(256) normalize_kernel(const float *__restrict_
     for (int j = lane; j < d; j += 32) {
         const float a = xr[j];
         out[row * d + j] = norm == CLEORA_NORM_NONE ? a : (norm == CLEORA_NORM_L2_RUST ? __fmul_rn(a, inv) : __fdiv_rn(a, nrm));
+    }
+}
+
+// The same normalisation as K1's fused epilogue (identical lane mapping and summation tree, hence identical bits) for
+// rows that were produced elsewhere -- the row-sharded half of the column-sharded multi-GPU loop -- with the
+// destinations of finish_row (local copy + column slices to their owners).
+template <int LPR, int VEC>
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__restrict__ x, int64_t n_rows, int norm,
+                                                             float *__restrict__ out, PeerOut peers) {
+    constexpr int RPW = 32 / LPR, D4 = LPR * VEC;
+    const int lane = threadIdx.x & 31, gl = lane & (LPR - 1);
+    const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+    const bool valid = row < n_rows;
+    float4 acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+        acc[v] = valid ? __ldg(reinterpret_cast<const float4 *>(x) + row * D4 + gl + v * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+    finish_row<LPR, VEC>(acc, row, valid, gl, out, nullptr, 1.f, 0.f, norm, peers);
+}
+
+template <int LPR, int VEC>
+static void launch_normalize_rows(const float *x, int64_t n, int norm, float *out, cudaStream_t st, const PeerOut &peers) {
+    const int64_t rows_per_block = 8 * (32 / LPR);
+    normalize_rows_kernel<LPR, VEC><<<(unsigned)((n + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(x, n, norm, out, peers);
+    LAUNCH_CHECK();
+}
+
+bool normalize_rows_supported(int64_t d) {
+    switch (d) { case 8: case 16: case 32: case 64: case 96: case 128: case 192: case 256: case 384: case 512: case 1024: return true; }
+    return false;
+}
+
+void launch_normalize_rows(const float *x, int64_t n, int64_t d, int norm, float *out, cudaStream_t st, const PeerOut *peers_in) {
+    if (n == 0 || d == 0) return;
+    PeerOut peers{};
+    if (peers_in) peers = *peers_in;
+    if (peers.mode == PEER_SLICES && (peers.slice_cols % 4 != 0 || (int64_t)peers.slice_cols * peers.n_extra != d))
+        throw CudaFail{"column slices must be multiples of 4 columns and cover the row"};
+    switch (d) {                                    // the lane mappings of launch_spmm
+        case 8:    launch_normalize_rows<2, 1>(x, n, norm, out, st, peers); return;
+        case 16:   launch_normalize_rows<4, 1>(x, n, norm, out, st, peers); return;
+        case 32:   launch_normalize_rows<8, 1>(x, n, norm, out, st, peers); return;
+        case 64:   launch_normalize_rows<16, 1>(x, n, norm, out, st, peers); return;
+        case 96:   launch_normalize_rows<8, 3>(x, n, norm, out, st, peers); return;
+        case 128:  launch_normalize_rows<32, 1>(x, n, norm, out, st, peers); return;
+        case 192:  launch_normalize_rows<16, 3>(x, n, norm, out, st, peers); return;
+        case 256:  launch_normalize_rows<32, 2>(x, n, norm, out, st, peers); return;
+        case 384:  launch_normalize_rows<32, 3>(x, n, norm, out, st, peers); return;
+        case 512:  launch_normalize_rows<32, 4>(x, n, norm, out, st, peers); return;
+        case 1024: launch_normalize_rows<32, 8>(x, n, norm, out, st, peers); return;
+        default: throw CudaFail{"row normaliser with destinations needs a vectorised feature dimension"};
     }
 }
 

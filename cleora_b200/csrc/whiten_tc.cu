@@ -5,12 +5,16 @@
 // A_hi*B_hi accumulated in fp32): the reference multiplies in f32 (np.dot), plain TF32 (10-bit mantissa) would
 // miss its 1e-5 bar.
 //
-// Shape: one CTA = 128 rows of x (UMMA M = 128), all N <= 256 output columns (UMMA N = N), K = d in chunks of 32.
+// Shape: one CTA = 128 rows of x (UMMA M = 128), all N output columns (one UMMA N = N <= 256 accumulator; 256 < N <= 512
+// runs the two column halves of a row tile as two passes into the two TMEM buffers), K = d in chunks of 32.
 // Warp roles (352 threads, persistent over row tiles):
 //   warps 0-3  A producers: thread = row; 128-bit loads of 32 floats, centre, split hi/lo, 16-byte stores into the
 //              canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices, LBO 128 B, SBO 1024 B);
-//   warps 4-7  epilogue: tcgen05.ld of the warp's 32 TMEM lanes (thread = row), optional row L2 norm, global stores
-//              (and, when asked, the same stores into the peers' copies);
+//   warps 4-7  epilogue: tcgen05.ld of the warp's 32 TMEM lanes (thread = row), optional row L2 norm, then every 32 x 32
+//              block goes through a padded shared-memory tile so that rows leave as 128-byte pieces, four rows per
+//              store instruction -- coalesced for HBM and, in the fused-collective modes (PeerOut), for NVLink: the
+//              same rows into the peers' copies (all-gather) or each 32-column slice into its owner's column-sharded
+//              matrix (all-to-all), 512 contiguous bytes per instruction;
 //   warp  8    TMEM allocation + MMA issuer (one elected lane): 3 x 4 tcgen05.mma per K chunk, tcgen05.commit to free
 //              smem stages and to publish the accumulator;
 //   warps 9-10 B loaders: the transform, pre-split and pre-tiled in global memory by prep_transform_kernel, is copied
@@ -33,6 +37,8 @@ constexpr int NMAX = 256;          // UMMA N limit
 constexpr int A_BYTES = BM * BK * 4;            // 16 KB (one of hi / lo)
 constexpr int B_LOAD_THREADS = 64;  // 2 loader warps for the transform
 constexpr int THREADS = 288 + B_LOAD_THREADS;
+constexpr int EPI_LD = 36;          // floats per row of an epilogue staging tile (32 + 4: conflict-free 128-bit rows)
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;   // one 32 x 32 tile per epilogue warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -137,14 +143,17 @@ __global__ void prep_transform_kernel(const float *__restrict__ T, int d, int do
 template <int NORM, int SCALED>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const float *__restrict__ mean,
-                       const float *__restrict__ rowscale, const float *__restrict__ Bt, int N,
+                       const float *__restrict__ rowscale, const float *__restrict__ Bt, int NT,
                        float *__restrict__ out, PeerOut peers) {
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int b_bytes = N * BK * 4;                                  // one of hi / lo
+    const int halves = NT > NMAX ? 2 : 1;                            // column halves of a row tile (two accumulator passes)
+    const int N = NT / halves;                                       // UMMA N
+    const int b_bytes = N * BK * 4;                                  // one of hi / lo, one half
     unsigned char *sA = smem_raw;                                    // STAGES x (A_hi, A_lo)
     unsigned char *sB = sA + STAGES * 2 * A_BYTES;                   // STAGES x (B_hi, B_lo)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * 2 * b_bytes);
+    float *sE = reinterpret_cast<float *>(sB + STAGES * 2 * b_bytes);   // epilogue staging tiles
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(sE) + EPI_BYTES);
     uint64_t *full_a = bars;                 // [STAGES] count 128
     uint64_t *full_b = bars + STAGES;        // [STAGES] count 1 + tx
     uint64_t *empty = bars + 2 * STAGES;     // [STAGES] count 1 (tcgen05.commit)
@@ -179,6 +188,7 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
             const bool in = row < n;
             const float4 *xr = reinterpret_cast<const float4 *>(x + (in ? row : 0) * (int64_t)d);
             const float rs = (SCALED && in) ? __ldg(rowscale + row) : 1.f;
+            for (int h = 0; h < halves; ++h)           // the second half re-reads the tile (L2) rather than keeping 2x the stages
             for (int c = 0; c < n_chunks; ++c, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -193,12 +203,12 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
                 for (int q = 0; q < 8; ++q) {
                     float4 m = __ldg(mp + q);
                     if (SCALED) { m.x = __fmul_rn(rs, m.x); m.y = __fmul_rn(rs, m.y); m.z = __fmul_rn(rs, m.z); m.w = __fmul_rn(rs, m.w); }
-                    float4 a, h, l;
+                    float4 a, hh, l;
                     a.x = in ? __fsub_rn(v[q].x, m.x) : 0.f; a.y = in ? __fsub_rn(v[q].y, m.y) : 0.f;
                     a.z = in ? __fsub_rn(v[q].z, m.z) : 0.f; a.w = in ? __fsub_rn(v[q].w, m.w) : 0.f;
-                    h.x = tf32_hi(a.x); h.y = tf32_hi(a.y); h.z = tf32_hi(a.z); h.w = tf32_hi(a.w);
-                    l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
-                    *reinterpret_cast<float4 *>(hi + off + q * 128) = h;
+                    hh.x = tf32_hi(a.x); hh.y = tf32_hi(a.y); hh.z = tf32_hi(a.z); hh.w = tf32_hi(a.w);
+                    l.x = a.x - hh.x; l.y = a.y - hh.y; l.z = a.z - hh.z; l.w = a.w - hh.w;
+                    *reinterpret_cast<float4 *>(hi + off + q * 128) = hh;
                     *reinterpret_cast<float4 *>(lo + off + q * 128) = l;
                 }
                 fence_proxy_async();                   // generic-proxy smem writes -> visible to the tensor core
@@ -209,28 +219,34 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
         // ------------------------------------------------------------------ epilogue (thread = row, own TMEM lane)
         const int q4 = warp - 4;                       // TMEM lane quarter of this warp
         const int r = q4 * 32 + lane;
-        uint32_t t = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-            const int buf = t & 1;
-            mbar_wait(&acc_full[buf], (t >> 1) & 1, 200);
+        float *tile_s = sE + q4 * 32 * EPI_LD;         // this warp's staging tile
+        const int sub = lane >> 3, c4 = lane & 7;      // store phase: lane -> (row within a group of 4, float4 column)
+        uint32_t t = 0;                                // accumulator passes consumed so far
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t row = tile * BM + r, row_w0 = tile * BM + q4 * 32;     // this thread's row; first row of the warp
+            uint32_t taddr[2];
+            for (int h = 0; h < halves; ++h) {
+                const uint32_t tt = t + h;
+                mbar_wait(&acc_full[tt & 1], (tt >> 1) & 1, 200);
+                taddr[h] = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((tt & 1) * NMAX);
+            }
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NMAX);
-            const int64_t row = tile * BM + r;
             float scale = 1.f;
             uint32_t v[32];
             if (NORM == CLEORA_NORM_L2_NUMPY) {
                 float ss = 0.f;
-                for (int c0 = 0; c0 < N; c0 += 32) {
-                    tmem_ld32(taddr + c0, v);
+                for (int h = 0; h < halves; ++h)
+                    for (int c0 = 0; c0 < N; c0 += 32) {
+                        tmem_ld32(taddr[h] + c0, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { const float f = __uint_as_float(v[j]); ss = fmaf(f, f, ss); }
-                }
+                        for (int j = 0; j < 32; ++j) { const float f = __uint_as_float(v[j]); ss = fmaf(f, f, ss); }
+                    }
                 scale = fmaxf(sqrtf(ss), 1e-10f);
             }
-            for (int c0 = 0; c0 < N; c0 += 32) {
-                tmem_ld32(taddr + c0, v);
-                if (row < n) {
-                    float4 *op = reinterpret_cast<float4 *>(out + row * (int64_t)N + c0);
+            for (int h = 0; h < halves; ++h)
+                for (int c0 = 0; c0 < N; c0 += 32) {
+                    tmem_ld32(taddr[h] + c0, v);
+                    __syncwarp();                              // the previous block has been read out of the tile
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 o;
@@ -240,62 +256,93 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
                             o.x = __fdiv_rn(o.x, scale); o.y = __fdiv_rn(o.y, scale);
                             o.z = __fdiv_rn(o.z, scale); o.w = __fdiv_rn(o.w, scale);
                         }
-                        op[j] = o;
+                        *reinterpret_cast<float4 *>(tile_s + lane * EPI_LD + 4 * j) = o;
+                    }
+                    __syncwarp();
+                    const int col0 = h * N + c0;               // first output column of this 32 x 32 block
+                    // SLICES mode: this lane's float4 column belongs to the rank that owns its column slice
+                    float *slice_ptr = nullptr;
+                    if (peers.mode == PEER_SLICES) {
+                        const int col = col0 + 4 * c4, owner = col / peers.slice_cols;
 #pragma unroll
-                        for (int p = 0; p < 7; ++p)                 // fused all-gather into the peers' copies
-                            if (p < peers.n_extra) reinterpret_cast<float4 *>(peers.extra[p] + row * (int64_t)N + c0)[j] = o;
+                        for (int p = 0; p < 8; ++p)
+                            if (p == owner) slice_ptr = peers.extra[p] + (col - owner * peers.slice_cols);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {              // 4 rows x 128 bytes per instruction
+                        const int rr = 4 * i + sub;
+                        const int64_t grow = row_w0 + rr;
+                        if (grow >= n) continue;
+                        const float4 o = *reinterpret_cast<const float4 *>(tile_s + rr * EPI_LD + 4 * c4);
+                        reinterpret_cast<float4 *>(out + grow * (int64_t)NT + col0)[c4] = o;
+                        if (peers.mode == PEER_SLICES) {
+                            *reinterpret_cast<float4 *>(slice_ptr + (peers.row_base + grow) * (int64_t)peers.slice_cols) = o;
+                        } else {
+#pragma unroll
+                            for (int p = 0; p < 7; ++p)        // fused all-gather into the peers' copies
+                                if (p < peers.n_extra) reinterpret_cast<float4 *>(peers.extra[p] + grow * (int64_t)NT + col0)[c4] = o;
+                        }
                     }
                 }
-            }
             tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);              // accumulator buffer may be overwritten
+            for (int h = 0; h < halves; ++h) mbar_arrive(&acc_empty[(t + h) & 1]);   // buffers may be overwritten
+            t += halves;
+            (void)row;
         }
     } else if (warp == 8) {
         // ------------------------------------------------------------------ MMA issuer
         const uint32_t idesc = make_idesc_tf32(BM, N);
         uint32_t it = 0, t = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-            const int buf = t & 1;
-            mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1, 100);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * NMAX);
-            for (int c = 0; c < n_chunks; ++c, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full_a[s], ph);
-                mbar_wait(&full_b[s], ph);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int h = 0; h < halves; ++h, ++t) {
+                const int buf = t & 1;
+                mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1, 100);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_hi = smem_u32(sA + s * 2 * A_BYTES), a_lo = a_hi + A_BYTES;
-                    const uint32_t b_hi = smem_u32(sB + s * 2 * b_bytes), b_lo = b_hi + b_bytes;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * NMAX);
+                for (int c = 0; c < n_chunks; ++c, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_a[s], ph);
+                    mbar_wait(&full_b[s], ph);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_hi = smem_u32(sA + s * 2 * A_BYTES), a_lo = a_hi + A_BYTES;
+                        const uint32_t b_hi = smem_u32(sB + s * 2 * b_bytes), b_lo = b_hi + b_bytes;
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {                 // UMMA K = 8 tf32 = two 16-byte core columns
-                        const uint32_t ko = k * 256;
-                        const uint64_t dah = make_desc(a_hi + ko, 128, 1024), dal = make_desc(a_lo + ko, 128, 1024);
-                        const uint64_t dbh = make_desc(b_hi + ko, 128, 1024), dbl = make_desc(b_lo + ko, 128, 1024);
-                        mma_tf32(tmem_d, dal, dbh, idesc, (c | k) != 0);   // small terms first
-                        mma_tf32(tmem_d, dah, dbl, idesc, 1);
-                        mma_tf32(tmem_d, dah, dbh, idesc, 1);
+                        for (int k = 0; k < BK / 8; ++k) {                 // UMMA K = 8 tf32 = two 16-byte core columns
+                            const uint32_t ko = k * 256;
+                            const uint64_t dah = make_desc(a_hi + ko, 128, 1024), dal = make_desc(a_lo + ko, 128, 1024);
+                            const uint64_t dbh = make_desc(b_hi + ko, 128, 1024), dbl = make_desc(b_lo + ko, 128, 1024);
+                            mma_tf32(tmem_d, dal, dbh, idesc, (c | k) != 0);   // small terms first
+                            mma_tf32(tmem_d, dah, dbl, idesc, 1);
+                            mma_tf32(tmem_d, dah, dbh, idesc, 1);
+                        }
+                        mma_commit(&empty[s]);                             // stage reusable once these MMAs retire
+                        if (c == n_chunks - 1) mma_commit(&acc_full[buf]); // accumulator complete
                     }
-                    mma_commit(&empty[s]);                             // stage reusable once these MMAs retire
-                    if (c == n_chunks - 1) mma_commit(&acc_full[buf]); // accumulator complete
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
         // ------------------------------------------------------------------ B loaders (cp.async, 2 warps)
         const int lt = threadIdx.x - 9 * 32;                    // 0..63
-        const int pieces = (2 * b_bytes) / 16;
+        const int plane_pieces = b_bytes / 16;                  // 16-byte pieces of one half of one plane
+        const int64_t plane_floats = (int64_t)NT * BK;          // one full-width plane of a chunk in the image
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int h = 0; h < halves; ++h)
             for (int c = 0; c < n_chunks; ++c, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 unsigned char *dst = sB + s * 2 * b_bytes;
-                const unsigned char *src = reinterpret_cast<const unsigned char *>(Bt + (int64_t)c * 2 * N * BK);
-                for (int p = lt; p < pieces; p += B_LOAD_THREADS) cp_async_cg16(dst + p * 16, src + p * 16);
+                // rows [h*N, (h+1)*N) of the chunk: 8-row groups are 1024 bytes apart in the image
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(Bt + (int64_t)c * 2 * plane_floats) + (size_t)h * b_bytes;
+                for (int p = lt; p < plane_pieces; p += B_LOAD_THREADS) {
+                    cp_async_cg16(dst + p * 16, src + p * 16);                                            // hi
+                    cp_async_cg16(dst + b_bytes + p * 16, src + plane_floats * 4 + p * 16);                // lo
+                }
                 cp_async_arrive_noinc(&full_b[s]);
             }
         }
@@ -311,7 +358,9 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
 }
 
 bool whiten_apply_tc_supported(int64_t d, int64_t dout) {
-    return d % tc::BK == 0 && d >= tc::BK && dout % 16 == 0 && dout >= 16 && dout <= tc::NMAX;
+    if (d % tc::BK != 0 || d < tc::BK || dout < 16) return false;
+    if (dout <= tc::NMAX) return dout % 32 == 0;                    // the epilogue moves 32-column blocks
+    return dout <= 2 * tc::NMAX && dout % 64 == 0;                  // two halves of <= 256 columns each
 }
 
 // Scratch for the pre-tiled transform lives in the caller's workspace (misc).
@@ -321,17 +370,20 @@ void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *m
     if (n == 0) return;
     PeerOut peers{};
     if (peers_in) peers = *peers_in;
+    if (peers.mode == PEER_SLICES && (peers.slice_cols % 4 != 0 || peers.slice_cols * peers.n_extra != dout))
+        throw CudaFail{"column slices must be multiples of 4 columns and cover the output"};
+    if (peers.mode == PEER_OWNERS) throw CudaFail{"tensor-core apply: unsupported destination mode"};
     float *Bt = (float *)workspace().misc.get((size_t)2 * d * dout * sizeof(float));
     const int64_t tot = d * dout;
     prep_transform_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(T, (int)d, (int)dout, Bt);
     LAUNCH_CHECK();
-    const int N = (int)dout;
-    const size_t smem = (size_t)STAGES * 2 * A_BYTES + (size_t)STAGES * 2 * N * BK * 4 + 16 * sizeof(uint64_t) + 16;
+    const int NT = (int)dout, N = NT > NMAX ? NT / 2 : NT;
+    const size_t smem = (size_t)STAGES * 2 * A_BYTES + (size_t)STAGES * 2 * N * BK * 4 + EPI_BYTES + 16 * sizeof(uint64_t) + 16;
     const int64_t n_tiles = (n + BM - 1) / BM;
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
     auto launch = [&](auto kernel) {
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, mean_f32, rowscale, Bt, N, out, peers);
+        kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, mean_f32, rowscale, Bt, NT, out, peers);
     };
     const bool l2 = norm == CLEORA_NORM_L2_NUMPY;
     if (norm != CLEORA_NORM_NONE && !l2) throw CudaFail{"tensor-core apply: unsupported fused normalisation"};

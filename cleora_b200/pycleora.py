@@ -108,6 +108,20 @@ class SparseMatrix:
         return SparseMatrix._adopt(h)
 
     @staticmethod
+    def from_hyperedge_arrays(members: np.ndarray, offsets: np.ndarray, columns: str = "complex::reflexive::node",
+                              hyperedge_trim_n: int = 16) -> "SparseMatrix":
+        """The graph ``from_iterator((" ".join(map(str, line)) for line in hyperedges), columns)`` builds, from a flat
+        member array and line offsets (hyperedge i = ``members[offsets[i]:offsets[i+1]]``), without Python strings."""
+        m = np.ascontiguousarray(members, dtype=np.uint32)
+        o = np.ascontiguousarray(offsets, dtype=np.int64)
+        if o.ndim != 1 or o.shape[0] < 1 or m.ndim != 1 or int(o[-1]) != m.shape[0]:
+            raise ValueError("offsets must have one entry per hyperedge plus one and end at len(members)")
+        h = C.c_void_p()
+        check(_lib.lib().cleora_graph_from_hyperedges(ptr(m, _lib.c_u32p), ptr(o, _lib.c_i64p), o.shape[0] - 1,
+                                                      columns.encode("utf-8"), int(hyperedge_trim_n), C.byref(h)))
+        return SparseMatrix._adopt(h)
+
+    @staticmethod
     def from_edge_arrays_device(src, dst, column_name: str = "node", shard_rank: int = 0, shard_world: int = 1,
                                 want_sym: bool = True, stream: int = 0) -> "SparseMatrix":
         """``from_edge_arrays`` on the GPU: ``src`` / ``dst`` are DEVICE arrays of 32-bit ids on the current device
@@ -196,8 +210,13 @@ class SparseMatrix:
             n, nnz = self.num_entities, self.num_edges
             rowptr, col = np.empty(n + 1, np.int64), np.empty(nnz, np.uint32)
             left, sym = np.empty(nnz, np.float32), np.empty(nnz, np.float32)
-            check(_lib.lib().cleora_graph_copy_csr(self._handle(), ptr(rowptr, _lib.c_i64p), ptr(col, _lib.c_u32p),
-                                                   ptr(left, _lib.c_f32p), ptr(sym, _lib.c_f32p)))
+            L, h = _lib.lib(), self._handle()
+            rc = L.cleora_graph_copy_csr(h, ptr(rowptr, _lib.c_i64p), ptr(col, _lib.c_u32p), ptr(left, _lib.c_f32p),
+                                         ptr(sym, _lib.c_f32p))
+            if rc == _lib.ERR_VALUE:             # built without symmetric values (adopted CSR / want_sym=False)
+                sym = None
+                rc = L.cleora_graph_copy_csr(h, ptr(rowptr, _lib.c_i64p), ptr(col, _lib.c_u32p), ptr(left, _lib.c_f32p), None)
+            check(rc)
             self._csr_cache = (rowptr, col, left, sym)
         return self._csr_cache
 
@@ -316,9 +335,17 @@ class SparseMatrix:
         d = int(feature_dim)
         if initial_embeddings is not None:
             x0 = np.ascontiguousarray(initial_embeddings, np.float32)
+            if x0.ndim != 2 or x0.shape[0] != self.num_entities:
+                raise ValueError(f"initial_embeddings has shape {tuple(x0.shape)} but graph has "
+                                 f"{self.num_entities} entities")
             d = x0.shape[1]
         if out is None:
             out = np.empty((self.num_entities, d), np.float32)
+        elif (not isinstance(out, np.ndarray) or out.dtype != np.float32 or out.shape != (self.num_entities, d)
+              or not out.flags["C_CONTIGUOUS"]):
+            raise ValueError(f"out must be a C-contiguous float32 array of shape ({self.num_entities}, {d})")
+        if timings is not None and (timings.dtype != np.float64 or timings.size < 8):
+            raise ValueError("timings must be a float64 array with at least 8 entries")
         done = C.c_int64(0)
         host = _lib.auto_host_eigh(self.num_entities, d, int(num_iterations), int(normalization), bool(whiten),
                                    float(residual_weight), float(convergence_threshold))

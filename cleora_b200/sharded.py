@@ -576,11 +576,24 @@ def embed_sharded(graph: SparseMatrix, feature_dim: int = 256, num_iterations: i
     if normalization not in norms:
         raise ValueError(f"Unknown normalization method: {normalization}. Use 'l2', 'l1', 'spectral', or 'none'.")
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    shard = Shard.from_matrix(graph, rank, world)
     d = feature_dim if initial_embeddings is None else initial_embeddings.shape[1]
     rust = initial_embeddings is None and normalization == "l2" and not whiten
-    em = ShardedEmbedder(shard, d, backend=backend, group=group)
     norm = _lib.NORM_L2_RUST if rust else norms[normalization]
+    from . import colsharded
+    if backend is None and colsharded.eligible(d, world):
+        # column-sharded SpMM with the transposes fused into the kernels' epilogues (colsharded.py): no all-gather
+        cem = colsharded.ColumnShardedEmbedder(graph, d, rank, world, group=group)
+        try:
+            if cem.pipeline_eligible(num_iterations, norm, residual_weight, convergence_threshold, whiten):
+                cem.run_pipelined(num_iterations, _lib.MARKOV[propagation], seed, initial_embeddings)
+            else:
+                cem.run(num_iterations, _lib.MARKOV[propagation], norm, seed, initial_embeddings, residual_weight,
+                        convergence_threshold, whiten, rust_semantics=rust)
+            return cem.result()
+        finally:
+            cem.close()
+    shard = Shard.from_matrix(graph, rank, world)
+    em = ShardedEmbedder(shard, d, backend=backend, group=group)
     if em.pipeline_eligible(num_iterations, norm, residual_weight, convergence_threshold, whiten):
         em.run_pipelined(num_iterations, _lib.MARKOV[propagation], seed, initial_embeddings)
     else:
@@ -609,41 +622,78 @@ class _Timers:
         return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in self.ev.items()}
 
 
-def bench(args, w, name, gen_pairs, spmm_bytes, measured_peaks, ClockSampler):
-    """bench.py's N>1 leg: strong scaling of the same workload, rows sharded over WORLD_SIZE GPUs."""
+def bench(args, w, name, build_host_graph, spmm_bytes, measured_peaks, ClockSampler):
+    """bench.py's N>1 leg: strong scaling of the same workload over WORLD_SIZE GPUs (one rank per GPU, NCCL).
+    Column-sharded loop (colsharded.py) where the shape allows it -- every rank then holds the whole CSR -- else the
+    row-sharded loop with its all-gather (CLEORA_B200_COLSHARD=0 forces the latter)."""
     import json
     import torch
     import torch.distributed as dist
+    from . import colsharded, pinned_empty, synth_pairs
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     d, iters = w["d"], args.iters
-    # rank 0 builds the CSR once; the others map it from /dev/shm
-    tag = f"/dev/shm/cleora_b200_{os.environ.get('MASTER_PORT', '0')}_{name}"
-    if rank == 0:
-        u, v = gen_pairs(w)
-        g = SparseMatrix.from_edge_arrays(u, v)
-        rowptr, col, left, sym = g._csr()
-        os.makedirs(tag, exist_ok=True)
-        for nm, a in (("rowptr", rowptr), ("col", col), ("left", left), ("sym", sym), ("hash", g.entity_hashes())):
-            np.save(os.path.join(tag, nm + ".npy"), a)
-        meta = [int(len(u))]
-    else:
-        meta = [0]
-    dist.barrier()
-    dist.broadcast_object_list(meta, src=0)
-    E = meta[0]
-    arrs = {nm: np.load(os.path.join(tag, nm + ".npy"), mmap_mode="r") for nm in ("rowptr", "col", "left", "sym", "hash")}
-    shard = Shard(arrs["rowptr"], arrs["col"], arrs["left"], arrs["sym"], arrs["hash"], rank, world)
-    n, nnz = shard.n, shard.nnz
-    em = ShardedEmbedder(shard, d)
-    check(em.be.L.cleora_dev_graph_prepare(shard.graph._handle()))
-    dist.barrier()
-    if rank == 0:
-        import shutil
-        shutil.rmtree(tag, ignore_errors=True)
-    norm = _lib.NORM_L2_NUMPY if args.whiten else _lib.NORM_L2_RUST
+    device_gen = bool(w.get("device_gen"))
+    cols = colsharded.eligible(d, world)
+    L = _lib.lib()
 
+    def build_device(u_d, v_d):
+        """(whole graph | this rank's row shard) on the device from the device-resident pair arrays."""
+        if cols:
+            return SparseMatrix.from_edge_arrays_device(u_d, v_d, want_sym=False)
+        return Shard.from_device_pairs(u_d, v_d, rank, world, want_sym=False)
+
+    if device_gen:
+        # every rank regenerates the same pair stream on its own GPU (counter-based generator) and builds what it needs
+        # there; nothing of the graph touches the host (cleora_dev_synth_pairs / cleora_dev_graph_from_pairs)
+        u_d, v_d = synth_pairs(w["kind"], w["n"], w["e"], w["seed"], w.get("alpha", 0.5))
+        obj = build_device(u_d, v_d)
+        E = int(w["e"])
+    else:
+        # rank 0 builds the CSR once; the others map it from /dev/shm
+        tag = f"/dev/shm/cleora_b200_{os.environ.get('MASTER_PORT', '0')}_{name}"
+        if rank == 0:
+            g0, n_edges = build_host_graph(w)
+            rowptr, col, left, sym = g0._csr()
+            os.makedirs(tag, exist_ok=True)
+            for nm, a in (("rowptr", rowptr), ("col", col), ("left", left), ("sym", sym), ("hash", g0.entity_hashes())):
+                np.save(os.path.join(tag, nm + ".npy"), a)
+            meta = [int(n_edges)]
+            del g0
+        else:
+            meta = [0]
+        dist.barrier()
+        dist.broadcast_object_list(meta, src=0)
+        E = meta[0]
+        arrs = {nm: np.load(os.path.join(tag, nm + ".npy"), mmap_mode="r") for nm in ("rowptr", "col", "left", "sym", "hash")}
+        if cols:
+            obj = SparseMatrix.from_csr(arrs["rowptr"], arrs["col"], arrs["left"], None, None, arrs["hash"])
+        else:
+            obj = Shard(arrs["rowptr"], arrs["col"], arrs["left"], arrs["sym"], arrs["hash"], rank, world)
+        dist.barrier()
+        if rank == 0:
+            import shutil
+            shutil.rmtree(tag, ignore_errors=True)
+
+    if cols:
+        graph = obj
+        n, nnz = graph.num_entities, graph.num_edges
+        em = colsharded.ColumnShardedEmbedder(graph, d, rank, world)
+        n_local, block = em.n_local, em.block
+    else:
+        shard = obj
+        if shard.nnz is None:
+            nnz_t = torch.tensor([shard.nnz_local], device="cuda", dtype=torch.int64)
+            dist.all_reduce(nnz_t)
+            shard.nnz = int(nnz_t.item())
+        n, nnz = shard.n, shard.nnz
+        em = ShardedEmbedder(shard, d)
+        graph = shard.graph
+        n_local, block = shard.n_local, shard.block
+    check(L.cleora_dev_graph_prepare(graph._handle()))
+    dist.barrier()
+    norm = _lib.NORM_L2_NUMPY if args.whiten else _lib.NORM_L2_RUST
     piped = em.pipeline_eligible(iters, norm, 0.0, 0.0, bool(args.whiten))
 
     def step(timers=None):
@@ -652,6 +702,9 @@ def bench(args, w, name, gen_pairs, spmm_bytes, measured_peaks, ClockSampler):
         else:
             em.run(iters, 0, norm, 0, None, 0.0, 0.0, bool(args.whiten), rust_semantics=not args.whiten, timers=timers)
 
+    def own_rows():
+        return em.result_rows[:n_local] if cols else em._own(em.x_full)[:n_local]
+
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -659,7 +712,7 @@ def bench(args, w, name, gen_pairs, spmm_bytes, measured_peaks, ClockSampler):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    launches0 = em.be.L.cleora_kernel_launch_count()
+    launches0 = L.cleora_kernel_launch_count()
     timers = _Timers(torch)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -673,68 +726,108 @@ def bench(args, w, name, gen_pairs, spmm_bytes, measured_peaks, ClockSampler):
     ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)                                     # max over ranks
     ms_step = float(ms.item()) / args.steps
-    launches = torch.tensor([em.be.L.cleora_kernel_launch_count() - launches0], device="cuda")
+    launches = torch.tensor([L.cleora_kernel_launch_count() - launches0], device="cuda")
     dist.all_reduce(launches)
     tot = timers.totals()
     phases = torch.tensor([tot.get(k, 0.0) for k in ("spmm", "stats", "eigh", "apply", "gather")], device="cuda")
     dist.all_reduce(phases, op=dist.ReduceOp.MAX)
-    # e2e: host CSR shard -> device (every step, same device buffers) -> loop -> this rank's rows of the result in
-    # pinned host memory.  The full result is the concatenation of the ranks' blocks; every rank writes its own block,
-    # as a sharded consumer would.  Timed per rank from a common barrier; the slowest rank counts.
-    from . import pinned_empty
-    own = pinned_empty((max(shard.block, 1), d), np.float32)
+
+    # e2e: inputs in host memory -> device -> loop -> this rank's rows of the result in pinned host memory.  The full
+    # result is the concatenation of the ranks' blocks; every rank writes its own block, as a sharded consumer would.
+    # Host-built workloads: the rank's CSR (its shard, or the whole CSR in the column-sharded loop) is re-copied into
+    # the same device buffers every step.  Device-built workloads: the edge list (pinned host memory on every rank) is
+    # uploaded and the device CSR is rebuilt every step.  Timed per rank from a common barrier; the slowest rank counts.
+    own = pinned_empty((max(block, 1), d), np.float32)
     own_t = torch.from_numpy(own)
+    if device_gen:
+        hu, hv = pinned_empty((E,), np.int32), pinned_empty((E,), np.int32)
+        torch.from_numpy(hu).copy_(u_d)
+        torch.from_numpy(hv).copy_(v_d)
     e2e_t = []
-    for i in range(1 + args.e2e_steps):
+    for i in range(1 + (max(1, args.e2e_steps - 1) if device_gen else args.e2e_steps)):
+        if device_gen:                               # free the previous device image before the rebuild
+            if cols:
+                em.graph = graph = None
+            else:
+                em.shard = None
+                shard.graph = graph = None
+            obj = None
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
-        check(em.be.L.cleora_graph_refresh_device(shard.graph._handle(), em.be.stream()))
+        if device_gen:
+            u_d.copy_(torch.from_numpy(hu), non_blocking=True)
+            v_d.copy_(torch.from_numpy(hv), non_blocking=True)
+            obj = build_device(u_d, v_d)
+            if cols:
+                em.graph = graph = obj
+                em.hash_ptr, _ = em.be.graph_hashes(graph)
+                em._rowscale_markov = None
+            else:
+                shard = obj
+                shard.nnz = nnz
+                em.shard, em.hash_pad, graph = shard, _DevPtr(shard.hash_ptr), shard.graph
+                if hasattr(em, "_pl"):
+                    em._pl["markov"] = None
+        else:
+            check(L.cleora_graph_refresh_device(graph._handle(), em.be.stream()))
         step()
-        own_t.copy_(em._own(em.x_full), non_blocking=True)
+        own_t[:n_local].copy_(own_rows(), non_blocking=True)
         torch.cuda.synchronize()
         if i > 0:
             e2e_t.append(time.perf_counter() - t0)
-    res = own[:shard.n_local]
+    res = own[:n_local]
     e2e = torch.tensor([sum(e2e_t) / len(e2e_t)], device="cuda")
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     clk = clocks.stop() if rank == 0 else None
     if rank == 0:
         peak, peak_src = measured_peaks()
         spmm_ms = float(phases[0].item()) / (iters * args.steps)
-        b_local = spmm_bytes(n, nnz, d) / world                                   # per-GPU share of the algorithmic bytes
+        if cols:        # per GPU: the whole CSR once + one column slice of the gathered rows + the slice of the product
+            ds = d // world
+            b_local = nnz * (8 + 4 * ds) + 8 * (n + 1) + 4 * n * ds
+            h2d = 8 * E if device_gen else 8 * (n + 1) + 8 * nnz + 8 * n
+        else:
+            b_local = spmm_bytes(n, nnz, d) / world
+            h2d = 8 * E if device_gen else 8 * (shard.n_local + 1) + 8 * shard.nnz_local + 8 * n
         achieved = b_local / (spmm_ms * 1e-3) / 1e9
         value = E * iters / (ms_step * 1e-3)
+        chol = em.be.chol_enabled(d) and bool(args.whiten)
         line = {
             "metric": "edges/sec through the 40-iteration embed() loop", "value": value, "unit": "edges/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic" + (" (generated and ingested on the device, per rank)" if device_gen else ""),
             "config": {"workload": name, "nodes": n, "edges": E, "nnz": nnz, "d": d, "iters": iters,
                        "whiten": bool(args.whiten), "pipeline_whiten": bool(piped),
                        "inner_whitening": ("Cholesky factor, computed redundantly on every rank (no broadcast); PCA eigh "
-                                           "on rank 0 + broadcast for the last iterate" if em.be.chol_enabled(d)
+                                           "on rank 0 + broadcast for the last iterate" if chol
                                            else "PCA eigh on rank 0 + broadcast every iteration"),
-                       "parallelism": f"row-shard x{world} (nnz-balanced)",
-                       "collectives": "NCCL all-gather of X blocks per iteration; all-reduce of d+d*d f64",
+                       "parallelism": (f"column-sharded SpMM x{world} (CSR replicated, {d // world} columns per GPU), dense "
+                                       f"stages row-sharded" if cols else f"row-shard x{world} (nnz-balanced)"),
+                       "collectives": ("two all-to-all transposes per iteration fused into the K1 / K3 epilogues (peer "
+                                       "stores over NVLink); all-reduce of d + d*d f64" if cols else
+                                       "NCCL all-gather of X blocks per iteration; all-reduce of d+d*d f64"),
                        "l2_flush": "inputs exceed the 126 MB L2"},
             "nnz_per_s": nnz * iters / (ms_step * 1e-3),
-            "e2e": {"value": E * iters / float(e2e.item()), "unit": "edges/s",
-                    "h2d_bytes_per_step": int(8 * (shard.n_local + 1) + 8 * shard.nnz_local + 8 * n),
-                    "d2h_bytes_per_step": int(4 * shard.n_local * d), "ms_per_step": 1e3 * float(e2e.item()),
+            "e2e": {"value": E * iters / float(e2e.item()), "unit": "edges/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(4 * n_local * d), "ms_per_step": 1e3 * float(e2e.item()),
                     "samples": len(e2e_t),
-                    "note": "per-rank bytes; each rank re-copies its CSR shard host->device and downloads its own rows "
-                            "of the result every step; X0 comes from the init kernel; max over ranks"},
+                    "note": "per-rank bytes; each rank re-copies its CSR host->device (device-generated workloads: uploads "
+                            "the edge list and rebuilds its CSR on the device) and downloads its own rows of the result "
+                            "every step; X0 comes from the init kernel; max over ranks"},
             "gpu_launches": int(launches.item()),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel (K1), per GPU", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "ms_per_launch": spmm_ms},
+                         "algorithmic_bytes_per_launch": b_local, "ms_per_launch": spmm_ms},
             "phase_ms_per_iter": {k: float(phases[i].item()) / (iters * args.steps)
                                   for i, k in enumerate(("spmm", "stats", "eigh", "apply", "gather"))},
-            "phase_note": "max over ranks; eigh (inner: Cholesky kernel) and gather run on side streams beside spmm / stats",
+            "phase_note": "max over ranks; eigh (inner: Cholesky kernel) runs on a side stream beside spmm; gather = "
+                          + ("the barrier after K1's scattered stores" if cols else "NCCL all-gather beside stats"),
             "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)
-        assert res.shape == (shard.n_local, d)
+        assert res.shape == (n_local, d)
     dist.barrier()
     dist.destroy_process_group()

@@ -76,6 +76,12 @@ int cleora_graph_from_files(const char *const *paths, int64_t n_paths, const cha
  * 2 to row_sum[u] (src/sparse_matrix_builder.rs:170-233). */
 int cleora_graph_from_pairs(const uint32_t *u, const uint32_t *v, int64_t n_pairs, const char *column_name,
                             cleora_graph_t **out);
+/* Integer hyperedges: line i has the members `members[offsets[i] .. offsets[i+1])` (ids of ONE column, given as
+ * integers; their decimal strings are the entity ids).  Exactly the graph cleora_graph_from_lines builds from the
+ * space-joined decimal strings under `columns` (e.g. "complex::reflexive::product"): same expansion, trimming and
+ * accumulation order (src/sparse_matrix_builder.rs:170-233), without building strings in the caller. */
+int cleora_graph_from_hyperedges(const uint32_t *members, const int64_t *offsets, int64_t n_lines, const char *columns,
+                                 int64_t hyperedge_trim_n, cleora_graph_t **out);
 /* The same ingest on the GPU (graph_dev.cu): `u`, `v` are DEVICE arrays on the current device; the CSR is built and
  * kept in HBM (no host copy: the 1.5 B-edge configuration has 24 GB of it; host accessors download on demand), bit for
  * bit the graph cleora_graph_from_pairs builds -- entity order, merged values, row sums, hashes.  shard_world > 1
@@ -151,7 +157,8 @@ int cleora_embed_fast(cleora_graph_t *g, int64_t d, int64_t iters, int markov, i
 int cleora_embed_fast_convergence(cleora_graph_t *g, int64_t d, int64_t max_iters, int markov, int64_t seed,
                                   float residual_weight, float convergence_threshold, float *out,
                                   int64_t *iters_done);
-/* whiten_embeddings (pycleora/__init__.py:130-164): x[n, d] -> out[n, n_components] (n_components <= 0: d). */
+/* whiten_embeddings (pycleora/__init__.py:130-164): x[n, d] -> out[n, n_components], 1 <= n_components <= d
+ * (CLEORA_ERR_VALUE otherwise; the binding resolves Python's None / slice semantics before the call). */
 int cleora_whiten_embeddings(const float *x, int64_t n, int64_t d, int64_t n_components, float *out);
 /* The loop body of embed() when it cannot take the Rust fast path (pycleora/__init__.py:97-125), kept on the
  * device for all iterations: propagate -> residual -> normalise -> whiten -> rmse early stop.
@@ -212,6 +219,26 @@ int cleora_dev_spmm_push(cleora_graph_t *g, int markov, const float *x, int64_t 
 int cleora_dev_whiten_apply_push(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
                                  int64_t dout, float *out, float *const *extra_outs, int n_extra, int normalization,
                                  const float *rowscale, void *stream);
+/* Column-sharded multi-GPU loop (cleora_b200/sharded.py: ColumnShardedEmbedder).  Every rank holds the WHOLE graph and a
+ * column slice X[:, g*ds .. (g+1)*ds) of the iterate; the dense stages run row-sharded (rank h owns rows
+ * [h*block_rows, (h+1)*block_rows)).  The two transposes between the layouts are all-to-alls fused into the producing
+ * kernels' epilogues as coalesced peer stores (`dests` are the ranks' buffers mapped through CUDA IPC, own buffer
+ * included, in rank order):
+ *  - cleora_dev_spmm_scatter: K1 on a slice x[n_cols, d] (d = ds); row r of the product is stored to
+ *    dests[r / block_rows] at row r % block_rows, columns [col_off, col_off + d) of an ld_cols-wide matrix.  No fused
+ *    row norm (the row is not complete here); residual mix as in cleora_dev_spmm with resid laid out like x.
+ *  - cleora_dev_whiten_apply_slices / cleora_dev_normalize_slices: K3 / K1's row normalisation on this rank's row
+ *    block x[n, d]; the full rows go to `out` and columns [h*ds, (h+1)*ds) of row r to dests[h] at row row_base + r of
+ *    an [n_total, ds] matrix, ds = dout / n_dst (a multiple of 4).  cleora_dev_normalize_slices with n_dst == 0 only
+ *    writes `out`. */
+int cleora_dev_spmm_scatter(cleora_graph_t *g, int markov, const float *x, int64_t d, float *const *dests, int n_dst,
+                            int64_t block_rows, int64_t ld_cols, int64_t col_off, const float *resid, float alpha,
+                            float rw, void *stream);
+int cleora_dev_whiten_apply_slices(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
+                                   int64_t dout, float *out, float *const *dests, int n_dst, int64_t row_base,
+                                   int normalization, const float *rowscale, void *stream);
+int cleora_dev_normalize_slices(const float *x, int64_t n, int64_t d, int normalization, float *out,
+                                float *const *dests, int n_dst, int64_t row_base, void *stream);
 /* Device memory that can be exported to the other ranks of the node (cudaMalloc + cudaIpc*); handles are 64 bytes. */
 int cleora_dev_malloc(size_t nbytes, void **out);
 int cleora_dev_free(void *p);
@@ -230,7 +257,8 @@ int cleora_dev_whiten_apply(const float *x, int64_t n, int64_t d, const float *m
                             int64_t dout, float *out, void *stream);
 /* K3 with the pipelined loop's extras: out = rownorm_or_not( (x - rowscale[r] * mean_f32) @ T ).  `rowscale` NULL = 1;
  * `normalization` CLEORA_NORM_NONE or CLEORA_NORM_L2_NUMPY (fused in the tensor-core epilogue; needs the tcgen05
- * shape rules d % 32 == 0, dout % 16 == 0, dout <= 256, otherwise CLEORA_ERR_VALUE). */
+ * shape rules d % 32 == 0 and either dout % 32 == 0, dout <= 256 or dout % 64 == 0, dout <= 512; otherwise
+ * CLEORA_ERR_VALUE). */
 int cleora_dev_whiten_apply_ex(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
                                int64_t dout, float *out, int normalization, const float *rowscale, void *stream);
 /* rowscale[r] = sum of the Markov values of row r (the vector A*1), f32 [n_rows], device. */

@@ -116,8 +116,10 @@ def test_hub_rows_are_split_deterministically():
     x128 = np.ascontiguousarray(x[:, :128])
     got128 = gs.left_markov_propagate(x128)
     np.testing.assert_array_equal(bits(got128[short]), bits(oracle.spmm(o, x128)[short]))
-    x32 = np.ascontiguousarray(x[:, :32])
-    np.testing.assert_array_equal(bits(gs.left_markov_propagate(x32)), bits(oracle.spmm(o, x32)))   # d=32: never split
+    x32 = np.ascontiguousarray(x[:, :32])                              # narrow rows (several rows per warp) split the same way
+    got32, ref32 = gs.left_markov_propagate(x32), oracle.spmm(o, x32)
+    np.testing.assert_array_equal(bits(got32[short]), bits(ref32[short]))
+    np.testing.assert_allclose(got32[~short], ref32[~short], rtol=1e-4, atol=1e-6 * np.abs(ref32).max())
 
 
 def test_push_epilogues_replicate_rows(er_pair):
@@ -151,6 +153,72 @@ def test_push_epilogues_replicate_rows(er_pair):
     torch.cuda.synchronize()
     np.testing.assert_allclose(zs[0].cpu().numpy(), ref, rtol=0, atol=2e-6)      # identity transform, unit rows
     assert torch.equal(zs[1], zs[0]) and torch.equal(zs[2], zs[0])
+
+
+@pytest.mark.parametrize("d,G", [(256, 8), (128, 8), (256, 2), (64, 4), (512, 8)])
+def test_fused_transposes_of_the_column_sharded_loop(er_pair, d, G):
+    """The three kernels behind cleora_b200/colsharded.py with all G "ranks" played by one process on one GPU (their
+    multi-process use over CUDA IPC is tests/test_gpu_sharded.py):
+      K1 on a column slice, rows scattered to the row owners  == the single product, bit for bit;
+      K1's row normalisation with column slices to the slice owners == the fused-norm single-GPU K1, bit for bit;
+      K3 with column slices == K3 (same kernel, other destinations), bit for bit."""
+    import ctypes as C
+    import torch
+    g, o = er_pair
+    L = _lib.lib()
+    n, ds = o.n, d // G
+    block = (n + G - 1) // G
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.cleora_dev_graph_prepare(g._handle()))
+    x = torch.from_numpy(np.random.default_rng(d + G).standard_normal((n, d)).astype(np.float32)).cuda()
+    ptrs = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])   # noqa: E731
+    # ---- B -> A: every rank's K1 on its slice, scattered into the owners' W buffers
+    wa = [torch.full((block, d), float("nan"), device="cuda") for _ in range(G)]
+    for r in range(G):
+        xs = x[:, r * ds:(r + 1) * ds].contiguous()
+        _lib.check(L.cleora_dev_spmm_scatter(g._handle(), 0, xs.data_ptr(), ds, ptrs(wa), G, block, d, r * ds, None, 1.0, 0.0, st))
+    torch.cuda.synchronize()
+    w = torch.cat(wa)[:n]
+    ref = torch.empty(n, d, device="cuda")
+    _lib.check(L.cleora_dev_spmm(g._handle(), 0, x.data_ptr(), d, ref.data_ptr(), None, 1.0, 0.0, _lib.NORM_NONE, st))
+    torch.cuda.synchronize()
+    assert torch.equal(w, ref)
+    np.testing.assert_array_equal(bits(w.cpu().numpy()), bits(oracle.spmm(o, x.cpu().numpy())))
+    # ---- A -> B: row normalisation of each row block, column slices to the slice owners
+    for norm in (_lib.NORM_L2_RUST, _lib.NORM_L2_NUMPY):
+        xb = [torch.full((block * G, ds), float("nan"), device="cuda") for _ in range(G)]
+        ya = [torch.empty(block, d, device="cuda") for _ in range(G)]
+        for h in range(G):
+            rows = min(block, max(0, n - h * block))
+            _lib.check(L.cleora_dev_normalize_slices(wa[h].data_ptr(), rows, d, norm, ya[h].data_ptr(), ptrs(xb), G, h * block, st))
+        fused = torch.empty(n, d, device="cuda")
+        _lib.check(L.cleora_dev_spmm(g._handle(), 0, x.data_ptr(), d, fused.data_ptr(), None, 1.0, 0.0, norm, st))
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat(ya)[:n], fused)                         # same summation tree as K1's fused epilogue
+        for r in range(G):
+            assert torch.equal(xb[r][:n], fused[:, r * ds:(r + 1) * ds])
+    # ---- A -> B through the tensor-core apply
+    if _lib.lib().cleora_whiten_apply_fusable(d, d):
+        rs = np.random.default_rng(1)
+        mean = torch.from_numpy((rs.standard_normal(d) * 1e-2).astype(np.float32)).cuda()
+        T = torch.from_numpy((rs.standard_normal((d, d)) / np.sqrt(d)).astype(np.float32)).cuda()
+        scale = torch.from_numpy(rs.uniform(0.9, 1.1, n).astype(np.float32)).cuda()
+        whole = torch.empty(n, d, device="cuda")
+        _lib.check(L.cleora_dev_whiten_apply_ex(w.data_ptr(), n, d, mean.data_ptr(), T.data_ptr(), d, whole.data_ptr(),
+                                                _lib.NORM_L2_NUMPY, scale.data_ptr(), st))
+        xb = [torch.full((block * G, ds), float("nan"), device="cuda") for _ in range(G)]
+        ya = [torch.empty(block, d, device="cuda") for _ in range(G)]
+        for h in range(G):
+            rows = min(block, max(0, n - h * block))
+            _lib.check(L.cleora_dev_whiten_apply_slices(wa[h].data_ptr(), rows, d, mean.data_ptr(), T.data_ptr(), d, ya[h].data_ptr(),
+                                                        ptrs(xb), G, h * block, _lib.NORM_L2_NUMPY,
+                                                        scale[h * block:].data_ptr() if rows else None, st))
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat(ya)[:n], whole)
+        for r in range(G):
+            assert torch.equal(xb[r][:n], whole[:, r * ds:(r + 1) * ds])
+        refz = oracle.normalize((w.cpu().numpy() - scale.cpu().numpy()[:, None] * mean.cpu().numpy()) @ T.cpu().numpy(), "l2")
+        assert scale_rel_err(whole.cpu().numpy(), refz) <= 1e-5
 
 
 def test_spmm_edge_cases():

@@ -7,6 +7,9 @@ Two launch modes, same worker:
     process's buffer), the three-stream pipelined choreography, the all-reduced statistics, the Cholesky-whitened inner
     iterations computed redundantly per rank, the final PCA transform + broadcast.
   * "nccl": one rank per visible GPU (2..8), NCCL over NVLink; skipped when fewer than two GPUs are visible.
+embed_sharded() picks the column-sharded loop (cleora_b200/colsharded.py: SpMM on column slices, both transposes fused
+into kernel epilogues as peer stores) when d splits evenly into supported slices -- world 2, 4, 8 for most cases below --
+and the row-sharded loop with its all-gather otherwise (world 3, d = 48), so both implementations are exercised.
 Bars: whiten=False is bit-identical to the single-GPU path for every rank count (accumulation order inside a row does
 not depend on the sharding); the whitened loop agrees with the single-GPU path and with the CPU oracle in
 Procrustes (<= 1e-4) and Gram (<= 1e-5) terms."""
@@ -109,7 +112,7 @@ def _check(outs):
                 assert gram_err(out, other) <= 1e-5, (kw, name)
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_sharded_ranks_sharing_one_gpu(world):
     _check(_run(world, "gloo"))
 

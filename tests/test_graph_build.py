@@ -75,6 +75,20 @@ def test_oracle_integer_ingest_equals_its_string_path():
     assert empty.n == 0 and empty.nnz == 0
 
 
+def test_integer_hyperedge_ingest_equals_string_path():
+    rs = np.random.default_rng(4)
+    k = np.minimum(1 + rs.poisson(3.0, 4000), 24)                            # some lines above the trim limit of 16
+    offsets = np.zeros(len(k) + 1, np.int64)
+    np.cumsum(k, out=offsets[1:])
+    members = rs.integers(0, 900, int(offsets[-1])).astype(np.uint32)
+    lines = [" ".join(str(int(t)) for t in members[offsets[i]:offsets[i + 1]]) for i in range(len(k))]
+    for trim in (16, 4):
+        gh = cb.SparseMatrix.from_hyperedge_arrays(members, offsets, "complex::reflexive::product", trim)
+        assert_same_graph(gh, oracle.build_graph(lines, "complex::reflexive::product", trim))
+    with pytest.raises(ValueError):
+        cb.SparseMatrix.from_hyperedge_arrays(members, offsets[:-1])
+
+
 def test_from_files(tmp_path):
     p1, p2 = tmp_path / "a.tsv", tmp_path / "b.txt"
     p1.write_text("u1\tp1 p2\n\nu2\tp2\r\n")
