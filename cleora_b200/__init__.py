@@ -131,9 +131,21 @@ def embed(
     _validate_propagation(propagation)
     if normalization not in ("l2", "l1", "none", "spectral"):
         raise ValueError(f"Unknown normalization method: {normalization}. Use 'l2', 'l1', 'spectral', or 'none'.")
-    if normalization == "spectral":
-        raise ValueError("normalization='spectral' is outside the accelerated path (an SVD per iteration); "
-                         "use 'l2', 'l1' or 'none'")
+    # normalization="spectral" (pycleora/__init__.py:951-956) = row l2 norm followed by a rotation of the iterate onto
+    # its right singular vectors.  The loop body is equivariant under orthogonal right-multiplication, so the loop runs
+    # with plain l2 and the rotation is applied to the iterates that leave it; with whiten=True the PCA whitening absorbs
+    # it altogether (checked against the reference's output in tests/test_gpu_parity.py).
+    spectral = normalization == "spectral"
+    if spectral:
+        normalization = "l2"
+
+    def _rotate(e):
+        if not spectral or whiten:
+            return e
+        out = np.empty_like(e)
+        check(_lib.lib().cleora_spectral_rotate(ptr(np.ascontiguousarray(e), _lib.c_f32p), e.shape[0], e.shape[1],
+                                                ptr(out, _lib.c_f32p)))
+        return out
     if initial_embeddings is not None:
         x0 = initial_embeddings.astype(np.float32)
         if x0.shape[0] != graph.num_entities:
@@ -146,10 +158,10 @@ def embed(
     # element-wise, so it depends on the eigensolver's sign conventions -- such calls use the reference's own LAPACK
     # eigh; the pipelined default loop also uses it (on the host, hidden behind the SpMM); otherwise cuSOLVER.
     lapack = whiten and convergence_threshold > 0 and _lib.eigh_mode() != "cusolver"
-    if callback is None:
+    if callback is None and not (spectral and not whiten and convergence_threshold > 0):
         out, _ = graph.embed_device(feature_dim, num_iterations, propagation, _DEVICE_NORMS[normalization], seed,
                                     x0, residual_weight, convergence_threshold, whiten)
-        return out
+        return _rotate(out) if num_iterations > 0 else out
 
     # per-iteration path: one device-resident iteration at a time so the callback sees every iterate
     embeddings = x0 if x0 is not None else graph.initialize_deterministically(feature_dim, seed)
@@ -158,7 +170,9 @@ def embed(
         with _lib.host_eigh(lapack):
             embeddings, _ = graph.embed_device(embeddings.shape[1], 1, propagation, _DEVICE_NORMS[normalization],
                                                seed, embeddings, residual_weight, 0.0, whiten)
-        callback(i, embeddings)
+            embeddings = _rotate(embeddings)
+        if callback is not None:
+            callback(i, embeddings)
         if convergence_threshold > 0 and i > 0:
             diff = embeddings.astype(np.float64, copy=False) - prev.astype(np.float64, copy=False)
             if float(np.sqrt(np.mean(diff * diff))) < convergence_threshold:   # _compute_rmse, :974-976

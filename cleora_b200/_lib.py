@@ -71,6 +71,7 @@ PROTOTYPES = {
     "cleora_embed_fast_convergence": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_float,
                                                 C.c_float, c_f32p, c_i64p]),
     "cleora_whiten_embeddings": (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int64, c_f32p]),
+    "cleora_spectral_rotate": (C.c_int, [c_f32p, C.c_int64, C.c_int64, c_f32p]),
     "cleora_embed": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_double,
                                C.c_int, C.c_int, c_f32p, c_i64p, c_f64p]),
     "cleora_set_eigh": (None, [EIGH_FN, C.c_void_p]),

@@ -307,14 +307,14 @@ int eigh_cusolver(double *a, double *w, int64_t d, void *) {
 }
 
 // pycleora/__init__.py:145-156: eigh -> descending order -> scale = 1/sqrt(max(lambda,1e-10)) -> (V*scale) as f32.
-void transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T) {
+void transform_from_cov(const double *cov, int64_t d, int64_t dout, float *T, bool scaled = true) {
     std::vector<double> a(cov, cov + d * d), w((size_t)d);
     const EighChoice eh = current_eigh();
     int rc = eh.fn ? eh.fn(a.data(), w.data(), d, eh.user) : eigh_cusolver(a.data(), w.data(), d, nullptr);
     if (rc != 0) throw std::runtime_error("eigh failed with code " + std::to_string(rc));
     std::vector<double> scale((size_t)dout);
     for (int64_t k = 0; k < dout; ++k)                          // argsort(eigenvalues)[::-1] on ascending input: column d-1-k
-        scale[(size_t)k] = 1.0 / std::sqrt(std::max(w[(size_t)(d - 1 - k)], 1e-10));
+        scale[(size_t)k] = scaled ? 1.0 / std::sqrt(std::max(w[(size_t)(d - 1 - k)], 1e-10)) : 1.0;
     for (int64_t i = 0; i < d; ++i) {
         const double *row = a.data() + i * d + (d - 1);
         float *t = T + i * dout;
@@ -341,14 +341,14 @@ struct DeviceEigh {
         work.alloc((size_t)std::max(lwork, 1));
     }
     // cov (d x d, symmetric, device) -> T (d x dout f32, device); everything enqueued on `st`.
-    void transform(const double *cov, int64_t d_, int64_t dout, float *T, cudaStream_t st) {
+    void transform(const double *cov, int64_t d_, int64_t dout, float *T, cudaStream_t st, bool scaled = true) {
         ensure(d_);
         if (cusolverDnSetStream(h, st) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("cusolverDnSetStream failed");
         CUDA_TRY(cudaMemcpyAsync(evec.p, cov, sizeof(double) * d * d, cudaMemcpyDeviceToDevice, st));
         if (cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)d, evec.p, (int)d, eval.p, work.p,
                              lwork, info.p) != CUSOLVER_STATUS_SUCCESS)
             throw std::runtime_error("cusolverDnDsyevd failed");
-        launch_build_transform(evec.p, eval.p, d, dout, T, st);
+        launch_build_transform(evec.p, eval.p, d, dout, T, st, scaled);
     }
     void check_info() {
         int hinfo = 0;
@@ -1184,6 +1184,34 @@ extern "C" int cleora_whiten_embeddings(const float *x, int64_t n, int64_t d, in
         WhitenState &ws = persistent().ws;
         Phase ph;
         whiten_device(dx.p, n, d, dout, dz.p, ws, nullptr, ph);
+        CUDA_TRY(cudaMemcpy(out, dz.p, dz.n * sizeof(float), cudaMemcpyDeviceToHost));
+        ws.eig.check_info();
+    });
+}
+
+// normalization="spectral" (pycleora/__init__.py:951-956): rows are l2-normalised (the caller does that in the loop) and
+// replaced by U*S of their SVD, i.e. rotated by the right singular vectors = the eigenvectors of X^T X in descending
+// order.  The loop body is equivariant under that rotation, so the binding applies it once, to the iterate that leaves
+// the loop (cleora_b200/__init__.py).  x, out: host [n, d].
+extern "C" int cleora_spectral_rotate(const float *x, int64_t n, int64_t d, float *out) {
+    return guarded([&] {
+        require_device();
+        if (n == 0 || d == 0) return;
+        DevBuf<float> dx((size_t)n * d), dz((size_t)n * d);
+        CUDA_TRY(cudaMemcpy(dx.p, x, dx.n * sizeof(float), cudaMemcpyHostToDevice));
+        WhitenState &ws = persistent().ws;
+        ws.ensure(d, d);
+        CUDA_TRY(cudaMemsetAsync(ws.sums.p, 0, sizeof(double) * d, nullptr));            // centre = 0: the Gram matrix X^T X
+        CUDA_TRY(cudaMemsetAsync(ws.mean32.p, 0, sizeof(float) * d, nullptr));
+        launch_centered_gram(dx.p, n, d, ws.sums.p, ws.cov.p, nullptr, nullptr);
+        if (current_eigh().fn) {
+            CUDA_TRY(cudaMemcpy(ws.h_cov.data(), ws.cov.p, sizeof(double) * d * d, cudaMemcpyDeviceToHost));
+            transform_from_cov(ws.h_cov.data(), d, d, ws.h_T.data(), false);
+            CUDA_TRY(cudaMemcpy(ws.T.p, ws.h_T.data(), sizeof(float) * d * d, cudaMemcpyHostToDevice));
+        } else {
+            ws.eig.transform(ws.cov.p, d, d, ws.T.p, nullptr, false);
+        }
+        launch_whiten_apply(dx.p, n, d, ws.mean32.p, ws.T.p, d, dz.p, nullptr);
         CUDA_TRY(cudaMemcpy(out, dz.p, dz.n * sizeof(float), cudaMemcpyDeviceToHost));
         ws.eig.check_info();
     });

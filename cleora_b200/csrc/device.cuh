@@ -124,7 +124,8 @@ void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *m
                             float *out, int norm, const float *rowscale, cudaStream_t st, const PeerOut *peers = nullptr);
 void launch_row_value_sums(const int64_t *rowptr, const float *val, int64_t n, float *out, cudaStream_t st);
 void launch_sq_diff_sum(const float *a, const float *b, int64_t n, bool f64_diff, double *result, cudaStream_t st);
-void launch_build_transform(const double *V, const double *w, int64_t d, int64_t dout, float *T, cudaStream_t st);
+void launch_build_transform(const double *V, const double *w, int64_t d, int64_t dout, float *T, cudaStream_t st,
+                            bool scaled = true);
 void launch_scale_f64(double *v, int64_t n, double factor, cudaStream_t st);
 void launch_f64_to_f32(const double *in, float *out, int64_t n, cudaStream_t st);
 // Device-side integer ingest and synthetic pair generators (graph_dev.cu).

@@ -87,6 +87,20 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// One lane of a converged warp, chosen by the hardware.  `if (lane == 0)` makes ptxas treat the operands of the
+// tcgen05.mma (descriptors, TMEM address: uniform-register operands) as possibly divergent and wrap EVERY MMA in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop -- ~11 extra instructions and >100 clk per MMA, which was the real limit of
+// both tensor-core kernels in round 1 (profiles/r2b_mma_probe_issue_bound.txt); under elect.sync it knows exactly one
+// lane is active and moves the values to uniform registers directly.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "@p mov.u32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
 
 // SWIZZLE_NONE descriptor; for MN-major operands LBO = byte distance between 8-row K groups, SBO = byte distance
 // between 16-byte MN groups (cute make_umma_desc<Major::MN>, INTERLEAVE case).
@@ -407,7 +421,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             }
             mbar_wait(&full[s], (st / PS) & 1);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t pbase = smem_u32(sP + s * stage_bytes);
                 uint32_t used = 0;                                    // bit g: accumulator already written this stage
 #pragma unroll

@@ -153,11 +153,13 @@ __device__ __forceinline__ void finish_row(float4 (&acc)[VEC], int64_t row, bool
     }
     if (valid) {
         if (peers.mode == PEER_OWNERS) {                      // column-sharded SpMM: the row belongs to another rank's block
-            const int64_t owner = row / peers.block_rows, local = row - owner * peers.block_rows;
+            // (row and block_rows are below 2^32: column indices are 32-bit, the matrix is square)
+            const uint32_t owner = (uint32_t)row / (uint32_t)peers.block_rows;
+            const int64_t local = row - (int64_t)owner * peers.block_rows;
             float4 *pp = nullptr;
 #pragma unroll
             for (int p = 0; p < 8; ++p)                       // static indices keep the pointers in the constant bank
-                if (p == owner) pp = reinterpret_cast<float4 *>(peers.extra[p] + local * peers.ld_cols + peers.col_off) + gl;
+                if ((uint32_t)p == owner) pp = reinterpret_cast<float4 *>(peers.extra[p] + local * peers.ld_cols + peers.col_off) + gl;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) pp[v * LPR] = acc[v];
             return;
@@ -969,19 +971,20 @@ void launch_sq_diff_sum(const float *a, const float *b, int64_t n, bool f64_diff
 // ================================================================================================ PCA transform
 // T[i, k] = V[i, d-1-k] / sqrt(max(w[d-1-k], 1e-10)) as f32 -- pycleora/__init__.py:147-156 (eigh returns ascending
 // eigenvalues; the reference re-orders descending).  V is column-major (cuSOLVER): V[i + c*d].
+// scaled == 0: the bare rotation V (descending order) -- normalization="spectral", pycleora/__init__.py:951-956.
 __global__ void build_transform_kernel(const double *__restrict__ V, const double *__restrict__ w, int d, int dout,
-                                       float *__restrict__ T) {
+                                       float *__restrict__ T, int scaled) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)d * dout) return;
     const int i = (int)(idx / dout), k = (int)(idx - (int64_t)i * dout);
     const int src = d - 1 - k;
-    const double scale = 1.0 / sqrt(fmax(w[src], 1e-10));
+    const double scale = scaled ? 1.0 / sqrt(fmax(w[src], 1e-10)) : 1.0;
     T[idx] = (float)(V[(int64_t)src * d + i] * scale);
 }
-void launch_build_transform(const double *V, const double *w, int64_t d, int64_t dout, float *T, cudaStream_t st) {
+void launch_build_transform(const double *V, const double *w, int64_t d, int64_t dout, float *T, cudaStream_t st, bool scaled) {
     const int64_t tot = d * dout;
     if (tot == 0) return;
-    build_transform_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(V, w, (int)d, (int)dout, T);
+    build_transform_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(V, w, (int)d, (int)dout, T, scaled ? 1 : 0);
     LAUNCH_CHECK();
 }
 

@@ -82,6 +82,20 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// One lane of a converged warp, chosen by the hardware.  `if (lane == 0)` makes ptxas treat the operands of the
+// tcgen05.mma (descriptors, TMEM address: uniform-register operands) as possibly divergent and wrap EVERY MMA in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop -- ~11 extra instructions and >100 clk per MMA, which was the real limit of
+// both tensor-core kernels in round 1 (profiles/r2b_mma_probe_issue_bound.txt); under elect.sync it knows exactly one
+// lane is active and moves the values to uniform registers directly.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "@p mov.u32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
 
 // Shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (Blackwell): start address, leading (K-direction) and
 // stride (M/N-direction 8-row group) byte offsets, all in 16-byte units.
@@ -305,7 +319,7 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
                     mbar_wait(&full_a[s], ph);
                     mbar_wait(&full_b[s], ph);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint32_t a_hi = smem_u32(sA + s * 2 * A_BYTES), a_lo = a_hi + A_BYTES;
                         const uint32_t b_hi = smem_u32(sB + s * 2 * b_bytes), b_lo = b_hi + b_bytes;
 #pragma unroll

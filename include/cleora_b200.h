@@ -160,6 +160,9 @@ int cleora_embed_fast_convergence(cleora_graph_t *g, int64_t d, int64_t max_iter
 /* whiten_embeddings (pycleora/__init__.py:130-164): x[n, d] -> out[n, n_components], 1 <= n_components <= d
  * (CLEORA_ERR_VALUE otherwise; the binding resolves Python's None / slice semantics before the call). */
 int cleora_whiten_embeddings(const float *x, int64_t n, int64_t d, int64_t n_components, float *out);
+/* normalization="spectral" (pycleora/__init__.py:951-956): out = x @ V, V = eigenvectors of x^T x (f64 Gram) in
+ * descending order -- U*S of the SVD of x up to column signs.  x is expected row-normalised; host [n, d]. */
+int cleora_spectral_rotate(const float *x, int64_t n, int64_t d, float *out);
 /* The loop body of embed() when it cannot take the Rust fast path (pycleora/__init__.py:97-125), kept on the
  * device for all iterations: propagate -> residual -> normalise -> whiten -> rmse early stop.
  * x0 == NULL: deterministic init from `seed`.  residual_weight is the Python float (double).  `x0` and `out` may

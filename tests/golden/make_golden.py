@@ -195,7 +195,7 @@ def er_lines(n, e, seed):
     return [f"{a} {b}" for a, b in zip(u[keep], v[keep])]
 
 
-def make_reference_runs():
+def make_reference_runs(only=None):
     ref, SM = import_reference()
     sys.path.insert(0, f"{REF}")
     karate = None
@@ -222,8 +222,15 @@ def make_reference_runs():
                           dict(feature_dim=32, num_iterations=5)),
         "er2k_d64_t8_now": (er_lines(2000, 12000, 12), "complex::reflexive::node",
                             dict(feature_dim=64, num_iterations=8, whiten=False)),
+        # normalization="spectral" (pycleora/__init__.py:951-956: row l2 norm, then U*S of the SVD = a rotation)
+        "karate_d8_t6_spectral_now": (karate["edges"], karate["columns"],
+                                      dict(feature_dim=8, num_iterations=6, normalization="spectral", whiten=False)),
+        "karate_d8_t6_spectral_w": (karate["edges"], karate["columns"],
+                                    dict(feature_dim=8, num_iterations=6, normalization="spectral")),
     }
     for name, (lines, columns, kw) in cases.items():
+        if only is not None and name not in only:
+            continue
         g = SM.from_iterator(iter(lines), columns)
         trace = []
         kw2 = dict(kw)
@@ -237,6 +244,8 @@ def make_reference_runs():
         np.savez_compressed(os.path.join(HERE, f"embed_{name}.npz"), **save)
         print(f"embed_{name}.npz written: out {out.shape}")
 
+    if only is not None:
+        return
     # callers that share the loop: multiscale taps, node-feature start, inductive warm start
     g = SM.from_iterator(iter(karate["edges"]), karate["columns"])
     ids = g.entity_ids
@@ -274,6 +283,9 @@ def make_reference_runs():
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (build container only)")
+    if len(sys.argv) > 1:                       # python make_golden.py <embed case> ...: (re)generate only those
+        make_reference_runs(only=set(sys.argv[1:]))
+        sys.exit(0)
     make_snapshots()
     make_xxh_kat()
     make_reference_runs()

@@ -426,6 +426,25 @@ def test_embed_variants_against_reference(golden_dir, name):
     assert procrustes_err(got, ref) <= 5e-3
 
 
+@pytest.mark.parametrize("name", ["karate_d8_t6_spectral_now", "karate_d8_t6_spectral_w"])
+def test_spectral_normalization_against_reference(golden_dir, name):
+    """normalization="spectral" (pycleora/__init__.py:951-956: row l2 norm, then U*S of the SVD).  The loop is
+    equivariant under that rotation, so the device loop runs plain l2 and rotates the iterate that leaves it
+    (cleora_spectral_rotate); with whiten=True the PCA whitening absorbs the rotation.  Raw agreement with the
+    unmodified reference's output after column-sign alignment."""
+    z = np.load(os.path.join(golden_dir, f"embed_{name}.npz"))
+    kw = ast.literal_eval(str(z["kwargs"]))
+    g = cb.SparseMatrix.from_iterator([str(s) for s in z["lines"]], str(z["columns"]))
+    got, ref = cb.embed(g, **kw), z["out"]
+    sign = np.sign(np.sum(got * ref, axis=0))
+    assert scale_rel_err(got * sign, ref) <= 1e-5
+    seen = []
+    got_cb = cb.embed(g, callback=lambda i, e: seen.append(e.copy()), **kw)           # per-iteration path
+    assert len(seen) == kw["num_iterations"]
+    sign = np.sign(np.sum(got_cb * ref, axis=0))
+    assert scale_rel_err(got_cb * sign, ref) <= 1e-5
+
+
 def test_teacher_forced_iteration_on_er_graph(er_pair):
     """One full default iteration from the ORACLE's iterate at t=3: SpMM+L2 <= 1e-6, then whitening compared
     through Gram/Procrustes."""

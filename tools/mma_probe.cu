@@ -64,7 +64,10 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int layout, int G, int re
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    if (tid == 0) {
+    uint32_t leader = 0;
+    if (tid < 32)                                     // elect.sync: see cleora_b200/csrc/gram_tc.cu (elect_one)
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p mov.u32 %0, 1;\n\t}" : "+r"(leader));
+    if (leader) {
         const bool mn = layout == 1 || layout == 3;
         const uint32_t idesc = make_idesc<KIND>(N, mn);
         // A occupies [0, 64 KB), B [64 KB, 192 KB).  One k-step of one MMA consumes 32 bytes of K per row.
