@@ -92,7 +92,7 @@ PROTOTYPES = {
                                           C.c_int64, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
     "cleora_dev_whiten_apply_slices": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                                  C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int, C.c_void_p,
-                                                 C.c_void_p]),
+                                                 C.c_int, C.c_void_p]),
     "cleora_dev_normalize_slices": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
                                               C.c_int, C.c_int64, C.c_void_p]),
     "cleora_dev_malloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -106,7 +106,7 @@ PROTOTYPES = {
     "cleora_dev_whiten_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_void_p, C.c_void_p]),
     "cleora_dev_whiten_apply_ex": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
-                                             C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+                                             C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "cleora_dev_row_scale": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "cleora_whiten_apply_fusable": (C.c_int, [C.c_int64, C.c_int64]),
     "cleora_dev_sq_diff_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),

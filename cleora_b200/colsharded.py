@@ -94,10 +94,11 @@ class ColumnBackend(CudaBackend):
                                              block, d, col_off, None if resid is None else resid.data_ptr(), alpha, rw,
                                              self.stream()))
 
-    def apply_slices(self, x, n, d, mean32, T, out, xb, row_base, norm, rowscale):
+    def apply_slices(self, x, n, d, mean32, T, out, xb, row_base, norm, rowscale, t_upper=False):
         check(self.L.cleora_dev_whiten_apply_slices(x.data_ptr(), n, d, mean32.data_ptr(), T.data_ptr(), d, out.data_ptr(),
                                                     self._ptrs(xb.dests), len(xb.dests), row_base, norm,
-                                                    None if rowscale is None else rowscale.data_ptr(), self.stream()))
+                                                    None if rowscale is None else rowscale.data_ptr(),
+                                                    1 if t_upper else 0, self.stream()))
 
     def normalize_slices(self, x, n, d, norm, out, xb, row_base):
         """K1's row normalisation of x[n, d] into `out`; with `xb` also every column slice into its owner's copy."""
@@ -331,7 +332,8 @@ class ColumnShardedEmbedder:
             self._spmm(markov, False, 1.0, 0.0, timers)               # W = A Y (needs no T)
             main.wait_stream(side)
             t = timers.start("apply") if timers else None
-            be.apply_slices(self.wa.tensor, self.n_local, d, self.mean32, self.T, y2, self.xb, self.r0, _lib.NORM_L2_NUMPY, rs_own)
+            be.apply_slices(self.wa.tensor, self.n_local, d, self.mean32, self.T, y2, self.xb, self.r0, _lib.NORM_L2_NUMPY, rs_own,
+                            inner_chol)
             if timers:
                 timers.stop(t)
             self._stats(y2, timers)                                   # its all-reduce: every rank's slices have landed

@@ -118,7 +118,7 @@ void free_device_graph(DeviceGraph *dg) {
     if (!dg) return;
     cudaFree(dg->rowptr); cudaFree(dg->col); cudaFree(dg->left); cudaFree(dg->sym); cudaFree(dg->hash);
     cudaFree(dg->long_rows); cudaFree(dg->long_chunk_ptr); cudaFree(dg->long_chunk_owner);
-    cudaFree(dg->rsum_left); cudaFree(dg->rsum_sym); cudaFree(dg->row_sum_all); cudaFree(dg->orig_ids);
+    cudaFree(dg->rsum_left); cudaFree(dg->rsum_sym); cudaFree(dg->row_sum_all); cudaFree(dg->orig_ids); cudaFree(dg->row_order);
     delete dg;
 }
 
@@ -139,6 +139,23 @@ void attach_long_row_schedule(DeviceGraph &d, const std::vector<int64_t> &rowptr
             for (int64_t c = 0; c < nc; ++c) owner.push_back((int32_t)rows.size());
             rows.push_back(r);
             cptr.push_back(cptr.back() + nc);
+        }
+    }
+    {   // degree-ordered row schedule for the kernels that put several (narrow) rows into one warp; only where the degrees
+        // are skewed enough to matter (counting sort by degree, descending, stable in the row index)
+        int64_t max_deg = 0;
+        for (int64_t r = 0; r < n_rows; ++r) max_deg = std::max(max_deg, rowptr[(size_t)r + 1] - rowptr[(size_t)r]);
+        const int64_t nnz = n_rows ? rowptr[(size_t)n_rows] : 0;
+        if (n_rows >= 1024 && n_rows < ((int64_t)1 << 32) && max_deg * n_rows > 4 * nnz && env_int64("CLEORA_B200_ROW_ORDER", 1) != 0) {
+            const int64_t cap = std::min<int64_t>(max_deg, 1 << 20);                 // degrees above the cap share the first bucket
+            std::vector<int64_t> start((size_t)cap + 2, 0);
+            auto bucket = [&](int64_t r) { return cap - std::min<int64_t>(rowptr[(size_t)r + 1] - rowptr[(size_t)r], cap); };
+            for (int64_t r = 0; r < n_rows; ++r) start[(size_t)bucket(r) + 1]++;
+            for (size_t b = 0; b + 1 < start.size(); ++b) start[b + 1] += start[b];
+            std::vector<uint32_t> order((size_t)n_rows);
+            for (int64_t r = 0; r < n_rows; ++r) order[(size_t)start[(size_t)bucket(r)]++] = (uint32_t)r;
+            CUDA_TRY(cudaMalloc((void **)&dg->row_order, order.size() * sizeof(uint32_t)));
+            CUDA_TRY(cudaMemcpy(dg->row_order, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
     }
     dg->long_threshold = threshold;
@@ -617,7 +634,7 @@ bool embed_pipelined_once(DeviceGraph &dg, const float *val, const float *rowsca
         }
         CUDA_TRY(cudaStreamWaitEvent(A, B.t_ready, 0));
         ph.begin();
-        launch_whiten_apply_tc(w, n, d, ws.mean32.p, ws.T.p, d, y2, CLEORA_NORM_L2_NUMPY, rowscale, A);
+        launch_whiten_apply_tc(w, n, d, ws.mean32.p, ws.T.p, d, y2, CLEORA_NORM_L2_NUMPY, rowscale, A, nullptr, inner_chol);
         ph.end(PH_APPLY);
         ph.begin();
         stats_device(y2, n, d, ws, A);
@@ -974,13 +991,13 @@ extern "C" int cleora_dev_spmm_scatter(cleora_graph_t *g, int markov, const floa
 }
 extern "C" int cleora_dev_whiten_apply_slices(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
                                               int64_t dout, float *out, float *const *dests, int n_dst, int64_t row_base,
-                                              int normalization, const float *rowscale, void *stream) {
+                                              int normalization, const float *rowscale, int t_upper, void *stream) {
     return guarded([&] {
         if (!whiten_apply_tc_supported(d, dout)) value_error("fused apply needs the tensor-core shape rules (see cleora_whiten_apply_fusable)");
         if (dout % n_dst != 0 || (dout / n_dst) % 4 != 0) value_error("column slices must be multiples of 4 columns");
         PeerOut peers = make_dests(dests, n_dst, PEER_SLICES);
         peers.slice_cols = (int)(dout / n_dst); peers.row_base = row_base;
-        launch_whiten_apply_tc(x, n, d, mean_f32, T, dout, out, normalization, rowscale, (cudaStream_t)stream, &peers);
+        launch_whiten_apply_tc(x, n, d, mean_f32, T, dout, out, normalization, rowscale, (cudaStream_t)stream, &peers, t_upper != 0);
     });
 }
 extern "C" int cleora_dev_normalize_slices(const float *x, int64_t n, int64_t d, int normalization, float *out,
@@ -1036,14 +1053,14 @@ extern "C" int cleora_dev_whiten_apply(const float *x, int64_t n, int64_t d, con
 }
 extern "C" int cleora_dev_whiten_apply_ex(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
                                           int64_t dout, float *out, int normalization, const float *rowscale,
-                                          void *stream) {
+                                          int t_upper, void *stream) {
     return guarded([&] {
         if (normalization == CLEORA_NORM_NONE && rowscale == nullptr) {
             launch_whiten_apply(x, n, d, mean_f32, T, dout, out, (cudaStream_t)stream);
             return;
         }
         if (!whiten_apply_tc_supported(d, dout)) value_error("fused apply needs d % 32 == 0 and dout % 32 == 0, dout <= 256 (or dout % 64 == 0, dout <= 512)");
-        launch_whiten_apply_tc(x, n, d, mean_f32, T, dout, out, normalization, rowscale, (cudaStream_t)stream);
+        launch_whiten_apply_tc(x, n, d, mean_f32, T, dout, out, normalization, rowscale, (cudaStream_t)stream, nullptr, t_upper != 0);
     });
 }
 extern "C" int cleora_dev_row_scale(cleora_graph_t *g, int markov, float *out, void *stream) {

@@ -28,6 +28,7 @@ struct DeviceGraph {
     int64_t *long_rows = nullptr;          // [n_long] row indices
     int64_t *long_chunk_ptr = nullptr;     // [n_long + 1] first chunk of each long row
     int32_t *long_chunk_owner = nullptr;   // [n_long_chunks] index into long_rows
+    uint32_t *row_order = nullptr;         // rows by descending degree (skewed graphs only): schedule of the narrow-row kernels
     float *rsum_left = nullptr, *rsum_sym = nullptr;   // A*1 per Markov type, built on first pipelined use
     // device-built graphs (graph_dev.cu): row sums of ALL entities, original integer ids by entity index, entity count
     // of the whole graph, and the number of entries in `hash` (n, or the padded row count of the gathered layout)
@@ -120,8 +121,10 @@ void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *me
 void launch_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
                          float *out, cudaStream_t st);
 bool whiten_apply_tc_supported(int64_t d, int64_t dout);
+// upper_triangular: T has no entries below the diagonal (the Cholesky whitening transform) -- lets K3 skip the zero blocks
 void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
-                            float *out, int norm, const float *rowscale, cudaStream_t st, const PeerOut *peers = nullptr);
+                            float *out, int norm, const float *rowscale, cudaStream_t st, const PeerOut *peers = nullptr,
+                            bool upper_triangular = false);
 void launch_row_value_sums(const int64_t *rowptr, const float *val, int64_t n, float *out, cudaStream_t st);
 void launch_sq_diff_sum(const float *a, const float *b, int64_t n, bool f64_diff, double *result, cudaStream_t st);
 void launch_build_transform(const double *V, const double *w, int64_t d, int64_t dout, float *T, cudaStream_t st,

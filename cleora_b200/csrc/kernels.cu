@@ -198,13 +198,18 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restric
                                                         const float *__restrict__ val, const float *__restrict__ x,
                                                         float *__restrict__ out, const float *__restrict__ resid,
                                                         int64_t n_rows, float alpha, float rw, int norm,
-                                                        int64_t long_threshold, PeerOut peers) {
+                                                        int64_t long_threshold, const uint32_t *__restrict__ order,
+                                                        PeerOut peers) {
     constexpr int RPW = 32 / LPR;          // rows per warp
     const int lane = threadIdx.x & 31;
     const int gl = lane & (LPR - 1);
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t row = warp * RPW + lane / LPR;
+    int64_t row = warp * RPW + lane / LPR;
     bool valid = row < n_rows;
+    // Several rows share a warp when the rows are narrow: walk them in degree order (skewed graphs only) so that the
+    // lane groups of a warp finish together -- on a power-law graph the warp otherwise runs as long as its longest row
+    // (measured on the products-shaped graph, 32-float slices: 27.2 ms in index order against 17.6 ms for full rows).
+    if (LPR < 32 && order != nullptr && valid) row = order[row];
     int64_t s = 0, e = 0;
     if (valid) { s = rowptr[row]; e = rowptr[row + 1]; }
     if (e - s > long_threshold) {                               // a hub row: the chunked kernels own it
@@ -341,7 +346,8 @@ static void launch_rows(const DeviceGraph &g, const float *val, const float *x, 
     const int64_t blocks = (g.n_rows + rows_per_block - 1) / rows_per_block;
     const bool split = g.n_long > 0;
     spmm_rows_kernel<LPR, VEC, U><<<(unsigned)blocks, threads, 0, st>>>(
-        g.rowptr, g.col, val, x, out, resid, g.n_rows, alpha, rw, norm, split ? g.long_threshold : INT64_MAX, peers);
+        g.rowptr, g.col, val, x, out, resid, g.n_rows, alpha, rw, norm, split ? g.long_threshold : INT64_MAX,
+        LPR < 32 ? g.row_order : nullptr, peers);
     LAUNCH_CHECK();
     if (split) {
         float *partial = (float *)workspace().spmm_partials.get((size_t)g.n_long_chunks * LPR * VEC * 4 * sizeof(float));

@@ -157,7 +157,7 @@ __global__ void prep_transform_kernel(const float *__restrict__ T, int d, int do
 template <int NORM, int SCALED>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const float *__restrict__ mean,
-                       const float *__restrict__ rowscale, const float *__restrict__ Bt, int NT,
+                       const float *__restrict__ rowscale, const float *__restrict__ Bt, int NT, int upper,
                        float *__restrict__ out, PeerOut peers) {
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -178,6 +178,13 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_chunks = d / BK;
     const int64_t n_tiles = (n + BM - 1) / BM;
+    // upper != 0: T is upper triangular (the Cholesky whitening transform): rows [32c, 32c+32) of T are zero left of
+    // column 32c, so K chunk c only touches the accumulator columns from n0(h, c) on -- the MMAs shrink to N - n0 columns
+    // (44 % fewer tensor clocks and operand bytes at d = 256) and steps with n0 >= N are skipped by every role.
+    auto first_col = [&](int h, int c) { return upper ? min(max(c * BK - h * N, 0), N) : 0; };
+    int steps_per_tile = 0;
+    for (int h = 0; h < halves; ++h)
+        for (int c = 0; c < n_chunks; ++c) steps_per_tile += first_col(h, c) < N ? 1 : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_a[s], 128); mbar_init(&full_b[s], B_LOAD_THREADS); mbar_init(&empty[s], 1); }
@@ -195,39 +202,62 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
 
     if (warp < 4) {
         // ------------------------------------------------------------------ A producers (thread = row of the tile)
+        // The global loads of step i+1 are issued before step i is converted: a producer that loads, waits and
+        // converts one chunk at a time spends most of each step in the load latency (ncu, round 2: the first use of the
+        // loaded data was the kernel's top stall and the tensor pipe idled 64 % of the time).
         const int r = threadIdx.x;                     // 0..127
-        uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int per_tile = halves * n_chunks;
+        const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t total = my_tiles * steps_per_tile;
+        auto advance = [&](int64_t &t, int &p) {       // next executed (half, chunk) step
+            do {
+                if (++p == per_tile) { p = 0; t += gridDim.x; }
+            } while (first_col(p / n_chunks, p % n_chunks) >= N);
+        };
+        float4 cur[8], nxt[8];
+        auto fetch = [&](int64_t tile, int c, float4 (&v)[8]) {
             const int64_t row = tile * BM + r;
             const bool in = row < n;
             const float4 *xr = reinterpret_cast<const float4 *>(x + (in ? row : 0) * (int64_t)d);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = in ? __ldg(xr + c * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        int64_t tile = blockIdx.x;
+        int pos = 0;                                    // position inside the tile's (half, chunk) sequence
+        if (total > 0) fetch(tile, 0, cur);
+        uint32_t it = 0;
+        for (int64_t i = 0; i < total; ++i, ++it) {
+            const int c = pos % n_chunks;
+            int64_t ntile = tile;
+            int npos = pos;
+            if (i + 1 < total) { advance(ntile, npos); fetch(ntile, npos % n_chunks, nxt); }
+            const int64_t row = tile * BM + r;
+            const bool in = row < n;
             const float rs = (SCALED && in) ? __ldg(rowscale + row) : 1.f;
-            for (int h = 0; h < halves; ++h)           // the second half re-reads the tile (L2) rather than keeping 2x the stages
-            for (int c = 0; c < n_chunks; ++c, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                float4 v[8];
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            const float4 *mp = reinterpret_cast<const float4 *>(mean + c * BK);
+            mbar_wait(&empty[s], ph ^ 1);              // stage free (first round passes immediately)
+            unsigned char *hi = sA + s * 2 * A_BYTES, *lo = hi + A_BYTES;
+            const int off = (r & 7) * 16 + (r >> 3) * 1024;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = in ? __ldg(xr + c * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 *mp = reinterpret_cast<const float4 *>(mean + c * BK);
-                mbar_wait(&empty[s], ph ^ 1);          // stage free (first round passes immediately)
-                unsigned char *hi = sA + s * 2 * A_BYTES, *lo = hi + A_BYTES;
-                const int off = (r & 7) * 16 + (r >> 3) * 1024;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 m = __ldg(mp + q);
-                    if (SCALED) { m.x = __fmul_rn(rs, m.x); m.y = __fmul_rn(rs, m.y); m.z = __fmul_rn(rs, m.z); m.w = __fmul_rn(rs, m.w); }
-                    float4 a, hh, l;
-                    a.x = in ? __fsub_rn(v[q].x, m.x) : 0.f; a.y = in ? __fsub_rn(v[q].y, m.y) : 0.f;
-                    a.z = in ? __fsub_rn(v[q].z, m.z) : 0.f; a.w = in ? __fsub_rn(v[q].w, m.w) : 0.f;
-                    hh.x = tf32_hi(a.x); hh.y = tf32_hi(a.y); hh.z = tf32_hi(a.z); hh.w = tf32_hi(a.w);
-                    l.x = a.x - hh.x; l.y = a.y - hh.y; l.z = a.z - hh.z; l.w = a.w - hh.w;
-                    *reinterpret_cast<float4 *>(hi + off + q * 128) = hh;
-                    *reinterpret_cast<float4 *>(lo + off + q * 128) = l;
-                }
-                fence_proxy_async();                   // generic-proxy smem writes -> visible to the tensor core
-                mbar_arrive(&full_a[s]);
+            for (int q = 0; q < 8; ++q) {
+                float4 m = __ldg(mp + q);
+                if (SCALED) { m.x = __fmul_rn(rs, m.x); m.y = __fmul_rn(rs, m.y); m.z = __fmul_rn(rs, m.z); m.w = __fmul_rn(rs, m.w); }
+                float4 a, hh, l;
+                a.x = in ? __fsub_rn(cur[q].x, m.x) : 0.f; a.y = in ? __fsub_rn(cur[q].y, m.y) : 0.f;
+                a.z = in ? __fsub_rn(cur[q].z, m.z) : 0.f; a.w = in ? __fsub_rn(cur[q].w, m.w) : 0.f;
+                hh.x = tf32_hi(a.x); hh.y = tf32_hi(a.y); hh.z = tf32_hi(a.z); hh.w = tf32_hi(a.w);
+                l.x = a.x - hh.x; l.y = a.y - hh.y; l.z = a.z - hh.z; l.w = a.w - hh.w;
+                *reinterpret_cast<float4 *>(hi + off + q * 128) = hh;
+                *reinterpret_cast<float4 *>(lo + off + q * 128) = l;
             }
+            fence_proxy_async();                       // generic-proxy smem writes -> visible to the tensor core
+            mbar_arrive(&full_a[s]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+            tile = ntile;
+            pos = npos;
         }
     } else if (warp < 8) {
         // ------------------------------------------------------------------ epilogue (thread = row, own TMEM lane)
@@ -313,7 +343,11 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
                 mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1, 100);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(buf * NMAX);
-                for (int c = 0; c < n_chunks; ++c, ++it) {
+                int last_c = 0;
+                for (int c = 0; c < n_chunks; ++c) if (first_col(h, c) < N) last_c = c;
+                for (int c = 0; c <= last_c; ++c, ++it) {                  // (steps right of last_c touch no column)
+                    const int n0 = first_col(h, c);
+                    const uint32_t idesc_c = upper ? make_idesc_tf32(BM, N - n0) : idesc;
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full_a[s], ph);
@@ -321,18 +355,19 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_hi = smem_u32(sA + s * 2 * A_BYTES), a_lo = a_hi + A_BYTES;
-                        const uint32_t b_hi = smem_u32(sB + s * 2 * b_bytes), b_lo = b_hi + b_bytes;
+                        const uint32_t b_hi = smem_u32(sB + s * 2 * b_bytes) + (uint32_t)(n0 / 8) * 1024u, b_lo = b_hi + b_bytes;
+                        const uint32_t tmem_c = tmem_d + (uint32_t)n0;
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k) {                 // UMMA K = 8 tf32 = two 16-byte core columns
                             const uint32_t ko = k * 256;
                             const uint64_t dah = make_desc(a_hi + ko, 128, 1024), dal = make_desc(a_lo + ko, 128, 1024);
                             const uint64_t dbh = make_desc(b_hi + ko, 128, 1024), dbl = make_desc(b_lo + ko, 128, 1024);
-                            mma_tf32(tmem_d, dal, dbh, idesc, (c | k) != 0);   // small terms first
-                            mma_tf32(tmem_d, dah, dbl, idesc, 1);
-                            mma_tf32(tmem_d, dah, dbh, idesc, 1);
+                            mma_tf32(tmem_c, dal, dbh, idesc_c, (c | k) != 0);   // small terms first
+                            mma_tf32(tmem_c, dah, dbl, idesc_c, 1);
+                            mma_tf32(tmem_c, dah, dbh, idesc_c, 1);
                         }
                         mma_commit(&empty[s]);                             // stage reusable once these MMAs retire
-                        if (c == n_chunks - 1) mma_commit(&acc_full[buf]); // accumulator complete
+                        if (c == last_c) mma_commit(&acc_full[buf]);       // accumulator complete
                     }
                     __syncwarp();
                 }
@@ -346,14 +381,17 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int h = 0; h < halves; ++h)
-            for (int c = 0; c < n_chunks; ++c, ++it) {
+            for (int c = 0; c < n_chunks; ++c) {
+                const int n0 = first_col(h, c);
+                if (n0 >= N) continue;                                     // nothing of this chunk lands in this half
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
+                ++it;
                 mbar_wait(&empty[s], ph ^ 1);
                 unsigned char *dst = sB + s * 2 * b_bytes;
-                // rows [h*N, (h+1)*N) of the chunk: 8-row groups are 1024 bytes apart in the image
+                // rows [h*N, (h+1)*N) of the chunk: 8-row groups are 1024 bytes apart in the image; rows below n0 are zero
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(Bt + (int64_t)c * 2 * plane_floats) + (size_t)h * b_bytes;
-                for (int p = lt; p < plane_pieces; p += B_LOAD_THREADS) {
+                for (int p = lt + (n0 / 8) * 64; p < plane_pieces; p += B_LOAD_THREADS) {
                     cp_async_cg16(dst + p * 16, src + p * 16);                                            // hi
                     cp_async_cg16(dst + b_bytes + p * 16, src + plane_floats * 4 + p * 16);                // lo
                 }
@@ -379,7 +417,8 @@ bool whiten_apply_tc_supported(int64_t d, int64_t dout) {
 
 // Scratch for the pre-tiled transform lives in the caller's workspace (misc).
 void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
-                            float *out, int norm, const float *rowscale, cudaStream_t st, const PeerOut *peers_in) {
+                            float *out, int norm, const float *rowscale, cudaStream_t st, const PeerOut *peers_in,
+                            bool upper_triangular) {
     using namespace tc;
     if (n == 0) return;
     PeerOut peers{};
@@ -397,7 +436,7 @@ void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *m
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
     auto launch = [&](auto kernel) {
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, mean_f32, rowscale, Bt, NT, out, peers);
+        kernel<<<grid, THREADS, smem, st>>>(x, n, (int)d, mean_f32, rowscale, Bt, NT, (upper_triangular && d == dout) ? 1 : 0, out, peers);
     };
     const bool l2 = norm == CLEORA_NORM_L2_NUMPY;
     if (norm != CLEORA_NORM_NONE && !l2) throw CudaFail{"tensor-core apply: unsupported fused normalisation"};

@@ -173,9 +173,10 @@ class CudaBackend:
     def fusable(self, d: int) -> bool:
         return bool(self.L.cleora_whiten_apply_fusable(d, d))
 
-    def apply_ex(self, x, n, d, mean32, T, out, norm, rowscale):
+    def apply_ex(self, x, n, d, mean32, T, out, norm, rowscale, t_upper=False):
         check(self.L.cleora_dev_whiten_apply_ex(x.data_ptr(), n, d, mean32.data_ptr(), T.data_ptr(), d, out.data_ptr(),
-                                                norm, None if rowscale is None else rowscale.data_ptr(), self.stream()))
+                                                norm, None if rowscale is None else rowscale.data_ptr(),
+                                                1 if t_upper else 0, self.stream()))
 
     def row_scale(self, shard, markov, out):
         check(self.L.cleora_dev_row_scale(shard.graph._handle(), markov, out.data_ptr(), self.stream()))
@@ -530,7 +531,7 @@ class ShardedEmbedder:
                 y2 = self._own(self.pm.buf[1 - self.cur])
                 be.apply_push(w, s.n_local, d, self.mean32, self.T, own_ptr, extra, _lib.NORM_L2_NUMPY, rowscale)
             else:
-                be.apply_ex(w, s.n_local, d, self.mean32, self.T, y2, _lib.NORM_L2_NUMPY, rowscale)
+                be.apply_ex(w, s.n_local, d, self.mean32, self.T, y2, _lib.NORM_L2_NUMPY, rowscale, inner_chol)
             if timers:
                 timers.stop(t)
             comm.wait_stream(main)

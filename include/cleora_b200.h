@@ -239,7 +239,7 @@ int cleora_dev_spmm_scatter(cleora_graph_t *g, int markov, const float *x, int64
                             float rw, void *stream);
 int cleora_dev_whiten_apply_slices(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
                                    int64_t dout, float *out, float *const *dests, int n_dst, int64_t row_base,
-                                   int normalization, const float *rowscale, void *stream);
+                                   int normalization, const float *rowscale, int t_upper, void *stream);
 int cleora_dev_normalize_slices(const float *x, int64_t n, int64_t d, int normalization, float *out,
                                 float *const *dests, int n_dst, int64_t row_base, void *stream);
 /* Device memory that can be exported to the other ranks of the node (cudaMalloc + cudaIpc*); handles are 64 bytes. */
@@ -261,9 +261,11 @@ int cleora_dev_whiten_apply(const float *x, int64_t n, int64_t d, const float *m
 /* K3 with the pipelined loop's extras: out = rownorm_or_not( (x - rowscale[r] * mean_f32) @ T ).  `rowscale` NULL = 1;
  * `normalization` CLEORA_NORM_NONE or CLEORA_NORM_L2_NUMPY (fused in the tensor-core epilogue; needs the tcgen05
  * shape rules d % 32 == 0 and either dout % 32 == 0, dout <= 256 or dout % 64 == 0, dout <= 512; otherwise
- * CLEORA_ERR_VALUE). */
+ * CLEORA_ERR_VALUE).  t_upper != 0 promises that T (d == dout) has no entries below the diagonal -- true for the
+ * transform of cleora_dev_chol_whiten -- and lets the kernel skip the zero blocks (about 44 % of the tensor work). */
 int cleora_dev_whiten_apply_ex(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T,
-                               int64_t dout, float *out, int normalization, const float *rowscale, void *stream);
+                               int64_t dout, float *out, int normalization, const float *rowscale, int t_upper,
+                               void *stream);
 /* rowscale[r] = sum of the Markov values of row r (the vector A*1), f32 [n_rows], device. */
 int cleora_dev_row_scale(cleora_graph_t *g, int markov, float *out, void *stream);
 /* 1 if cleora_dev_whiten_apply_ex can fuse (tensor-core path available for this shape), else 0. */

@@ -98,7 +98,7 @@ class OracleColumnBackend:
     def normalize_slices(self, x, n, d, norm, out, xb, row_base):
         self._slices(self._norm(np.array(x.numpy()[:n]), norm), out, xb, row_base, n)
 
-    def apply_slices(self, x, n, d, mean32, T, out, xb, row_base, norm, rowscale):
+    def apply_slices(self, x, n, d, mean32, T, out, xb, row_base, norm, rowscale, t_upper=False):
         rs = np.ones((n, 1), np.float32) if rowscale is None else rowscale.numpy()[:n, None]
         q = (np.array(x.numpy()[:n]) - rs * mean32.numpy()) @ T.numpy()
         self._slices(self._norm(q, norm), out, xb, row_base, n)

@@ -205,14 +205,14 @@ def test_fused_transposes_of_the_column_sharded_loop(er_pair, d, G):
         scale = torch.from_numpy(rs.uniform(0.9, 1.1, n).astype(np.float32)).cuda()
         whole = torch.empty(n, d, device="cuda")
         _lib.check(L.cleora_dev_whiten_apply_ex(w.data_ptr(), n, d, mean.data_ptr(), T.data_ptr(), d, whole.data_ptr(),
-                                                _lib.NORM_L2_NUMPY, scale.data_ptr(), st))
+                                                _lib.NORM_L2_NUMPY, scale.data_ptr(), 0, st))
         xb = [torch.full((block * G, ds), float("nan"), device="cuda") for _ in range(G)]
         ya = [torch.empty(block, d, device="cuda") for _ in range(G)]
         for h in range(G):
             rows = min(block, max(0, n - h * block))
             _lib.check(L.cleora_dev_whiten_apply_slices(wa[h].data_ptr(), rows, d, mean.data_ptr(), T.data_ptr(), d, ya[h].data_ptr(),
                                                         ptrs(xb), G, h * block, _lib.NORM_L2_NUMPY,
-                                                        scale[h * block:].data_ptr() if rows else None, st))
+                                                        scale[h * block:].data_ptr() if rows else None, 0, st))
         torch.cuda.synchronize()
         assert torch.equal(torch.cat(ya)[:n], whole)
         for r in range(G):
@@ -361,6 +361,30 @@ def test_apply_transform_given_identical_T(n, d, dout):
                                          torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert scale_rel_err(out.cpu().numpy(), ref) <= 1e-5
+
+
+@pytest.mark.parametrize("n,d", [(5000, 256), (3000, 128), (4097, 512), (1000, 64)])
+def test_apply_with_upper_triangular_transform(n, d):
+    """K3's zero-block skipping for an upper-triangular T (the Cholesky whitening transform) against the dense path of the
+    same kernel and against numpy."""
+    import torch
+    rs = np.random.default_rng(d + 1)
+    x = oracle.normalize(rs.standard_normal((n, d)).astype(np.float32))
+    mean = (rs.standard_normal(d) * 1e-2).astype(np.float32)
+    T = np.triu(rs.standard_normal((d, d)) / np.sqrt(d)).astype(np.float32)
+    L = _lib.lib()
+    xd, md, Td = (torch.from_numpy(a).cuda() for a in (x, mean, np.ascontiguousarray(T)))
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for upper in (0, 1):
+        out = torch.empty(n, d, dtype=torch.float32, device="cuda")
+        _lib.check(L.cleora_dev_whiten_apply_ex(xd.data_ptr(), n, d, md.data_ptr(), Td.data_ptr(), d, out.data_ptr(),
+                                                _lib.NORM_L2_NUMPY, None, upper, st))
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    ref = oracle.normalize((x - mean) @ T, "l2")
+    assert scale_rel_err(outs[0], ref) <= 1e-5 and scale_rel_err(outs[1], ref) <= 1e-5
+    assert scale_rel_err(outs[1], outs[0]) <= 2e-7                      # only exact zeros were skipped
 
 
 def test_whiten_embeddings_matches_reference_golden(golden_dir):

@@ -86,7 +86,7 @@ class OracleBackend:
     def fusable(self, d):
         return True
 
-    def apply_ex(self, x, n, d, mean32, T, out, norm, rowscale):
+    def apply_ex(self, x, n, d, mean32, T, out, norm, rowscale, t_upper=False):
         rs = np.ones((n, 1), np.float32) if rowscale is None else rowscale.numpy()[:n, None]
         q = (x.numpy()[:n] - rs * mean32.numpy()) @ T.numpy()
         if norm == _lib.NORM_L2_NUMPY:
