@@ -50,7 +50,7 @@ class CudaPeerBuffer:
     ``dests`` the addresses of all ranks' buffers in rank order (own one included) as mapped into this process."""
 
     def __init__(self, be, rows, cols, dist, group, rank, world):
-        self.be, self.L = be, be.L
+        self.be, self.L, self._dist, self._group = be, be.L, dist, group
         nbytes = max(rows * cols * 4, 4)
         p = C.c_void_p()
         check(self.L.cleora_dev_malloc(nbytes, C.byref(p)))
@@ -72,10 +72,15 @@ class CudaPeerBuffer:
         self.tensor.zero_()
 
     def close(self):
+        """Collective: every rank unmaps the peers' buffers, THEN the owners free them (freeing an exported allocation
+        while another process still has it mapped is undefined behaviour in CUDA IPC)."""
+        self.be.torch.cuda.synchronize()
         for q in self._opened:
             self.L.cleora_ipc_close(q)
         self._opened = []
+        self._dist.barrier(group=self._group)
         if self.ptr:
+            self.tensor = None
             self.L.cleora_dev_free(self.ptr)
             self.ptr = None
 

@@ -141,19 +141,24 @@ void attach_long_row_schedule(DeviceGraph &d, const std::vector<int64_t> &rowptr
             cptr.push_back(cptr.back() + nc);
         }
     }
-    {   // degree-ordered row schedule for the kernels that put several (narrow) rows into one warp; only where the degrees
-        // are skewed enough to matter (counting sort by degree, descending, stable in the row index)
+    {   // Row schedule for the kernels that put several (narrow) rows into one warp: inside windows of 4096 consecutive
+        // rows the rows are visited by descending degree, so the lane groups of a warp get rows of similar length, while
+        // the CSR is still streamed window by window (a global degree order was measured slower: it turns the col/val
+        // stream into random ~100-byte segments).  Only where the degrees are skewed enough to matter.
         int64_t max_deg = 0;
         for (int64_t r = 0; r < n_rows; ++r) max_deg = std::max(max_deg, rowptr[(size_t)r + 1] - rowptr[(size_t)r]);
         const int64_t nnz = n_rows ? rowptr[(size_t)n_rows] : 0;
         if (n_rows >= 1024 && n_rows < ((int64_t)1 << 32) && max_deg * n_rows > 4 * nnz && env_int64("CLEORA_B200_ROW_ORDER", 1) != 0) {
-            const int64_t cap = std::min<int64_t>(max_deg, 1 << 20);                 // degrees above the cap share the first bucket
-            std::vector<int64_t> start((size_t)cap + 2, 0);
-            auto bucket = [&](int64_t r) { return cap - std::min<int64_t>(rowptr[(size_t)r + 1] - rowptr[(size_t)r], cap); };
-            for (int64_t r = 0; r < n_rows; ++r) start[(size_t)bucket(r) + 1]++;
-            for (size_t b = 0; b + 1 < start.size(); ++b) start[b + 1] += start[b];
+            const int64_t window = env_int64("CLEORA_B200_ROW_WINDOW", 4096);
             std::vector<uint32_t> order((size_t)n_rows);
-            for (int64_t r = 0; r < n_rows; ++r) order[(size_t)start[(size_t)bucket(r)]++] = (uint32_t)r;
+            #pragma omp parallel for schedule(static)
+            for (int64_t w0 = 0; w0 < n_rows; w0 += window) {
+                const int64_t w1 = std::min(n_rows, w0 + window);
+                for (int64_t r = w0; r < w1; ++r) order[(size_t)r] = (uint32_t)r;
+                std::stable_sort(order.begin() + w0, order.begin() + w1, [&](uint32_t a, uint32_t b) {
+                    return rowptr[(size_t)a + 1] - rowptr[(size_t)a] > rowptr[(size_t)b + 1] - rowptr[(size_t)b];
+                });
+            }
             CUDA_TRY(cudaMalloc((void **)&dg->row_order, order.size() * sizeof(uint32_t)));
             CUDA_TRY(cudaMemcpy(dg->row_order, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }

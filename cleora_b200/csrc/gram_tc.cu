@@ -17,17 +17,18 @@
 //
 // One CTA = a 128 x 64 output tile (row block i, column stripe j at or right of block i -- every G_s is symmetric, the
 // combine kernel mirrors the rest) for a slice of rows: TMEM holds the 7 weight-group accumulators of 128 x 64 int32 =
-// 448 of its 512 columns.  Per 32-row stage: 8 converter warps read the rows straight from global memory (128-bit
-// read-only loads, the next stage prefetched into registers while the current one is converted), quantise all d columns
-// into four byte planes in a canonical no-swizzle UMMA layout (MN-major for d = 256, K-major for d = 128), one elected
-// lane issues the 16 tcgen05.mma (both operands are views of the planes: A = the 128 columns of block i in plane k,
-// B = the stripe's 64 columns in plane l), and 4 drain warps move the accumulators to int64 global memory every 192
-// stages.
-// Shared memory is the resource that bounds this kernel (ncu, round 2: 186 M LSU/LDGSTS wavefronts + 96 KB of MMA operand
-// reads per stage against a 128 B/clk port; the tensor pipe itself issues a 128x64x32 MMA every 48 clk,
-// profiles/r2c_mma_probe.txt).  Round 1 staged the raw f32 rows in shared memory first (cp.async ring, 4 loader warps):
-// 64 KB of extra shared-memory traffic per stage plus LDGSTS bank conflicts -- removed here, which also frees 133 KB
-// for four plane stages instead of two.
+// 448 of its 512 columns.  Per 32-row stage: 4 loader warps stage the rows (cp.async, 4 stages deep), 8 converter warps
+// quantise all d columns into four byte planes in a canonical no-swizzle UMMA layout (MN-major for d = 256, K-major
+// for d = 128), one lane issues the 16 tcgen05.mma (both operands are views of the planes: A = the 128 columns of block
+// i in plane k, B = the stripe's 64 columns in plane l), and 4 drain warps move the accumulators to int64 global memory
+// every 192 stages.
+// Round-2 measurements (profiles/r2d_*): the shared-memory port bounds this kernel, not the tensor pipe (which issues a
+// 128x64x32 MMA every 48 clk with both operands in shared memory, profiles/r2c_mma_probe.txt): per 32-row stage the
+// cp.async ring writes 32 KB, the converters read it and write 32 KB of planes, and the 16 MMAs read 96 KB of operands
+// -- ~1900 wavefronts of a 128 B/clk port against 773 clk of MMA.  Letting the converters read global memory directly
+// (no ring) was tried and is slower (2.3 vs 1.8 ms at C2): the loads then occupy the same L1/shared-memory pipeline with
+// worse sector efficiency.  The step that would help is the A operand in TMEM (tcgen05.cp once per plane, 32 clk per
+// MMA): see DESIGN.md section 9.
 #include "device.cuh"
 #include "../../include/cleora_b200.h"
 
@@ -44,9 +45,11 @@ constexpr int STRIPE = 64;         // output columns per CTA (UMMA N); the CTA o
 constexpr int GROUPS = 7;          // weight groups s = k + l
 constexpr int DRAIN_STAGES = 192;  // 192*32 = 6144 rows: 4 * 255^2 * 6144 < 2^31
 constexpr int CONV_THREADS = 256;  // 8 converter warps (16 were tried with the K-major converter: +7 % only)
-constexpr int THREADS = CONV_THREADS + 128 + 32;   // + 4 drain warps + MMA warp
-constexpr int PS = 4;              // plane stages; compile-time: a runtime modulo in the per-stage bookkeeping cost
-                                   // every role ~10 % (measured 2.10 -> 1.88 ms)
+constexpr int LOAD_THREADS = 128;  // 4 loader warps (cp.async, fully coalesced)
+constexpr int THREADS = CONV_THREADS + 128 + 32 + LOAD_THREADS;   // + 4 drain warps + MMA warp + loaders
+constexpr int PS = 2;              // plane stages; compile-time, like RAW_STAGES: a runtime modulo in the per-stage
+                                   // bookkeeping cost every role ~10 % (measured 2.10 -> 1.88 ms)
+constexpr int RAW_STAGES = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -207,8 +210,18 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int plane_bytes = ROWS * d;                                 // one byte plane of one stage
     const int stage_bytes = 4 * plane_bytes;
-    unsigned char *sP = smem_raw;                                     // [PS] byte planes (MMA operands)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + PS * stage_bytes);
+    // Raw rows are staged densely (row stride d*4, every cp.async piece 16-byte aligned inside its 128-byte line) with
+    // an XOR swizzle: piece p of stage row r lives at piece p ^ (r & 7).  Eight converter lanes that read the same
+    // piece index of eight consecutive rows then hit eight different 16-byte slots (conflict-free LDS.128), and a
+    // loader quarter-warp still fills exactly one 128-byte line.  (Round 1 skewed the rows by 16 bytes instead, which
+    // kept the LDS conflict-free but made most LDGSTS quarter-warps straddle two lines: 102 M wavefronts for 48 M ideal.)
+    const int raw_stride = d * 4;
+    const int raw_bytes = ROWS * raw_stride;
+    unsigned char *sP = smem_raw;                                     // [STAGES] byte planes (MMA operands)
+    unsigned char *sR = sP + PS * stage_bytes;                        // [RAW_STAGES] raw f32 rows (cp.async ring)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sR + RAW_STAGES * raw_bytes);
+    uint64_t *raw_full = bars;                   // [RAW_STAGES] count LOAD_THREADS (cp.async noinc arrivals)
+    uint64_t *raw_empty = bars + MAX_STAGES;     // [RAW_STAGES] count CONV_THREADS
     uint64_t *full = bars + 2 * MAX_STAGES;      // [PS] count CONV_THREADS: planes ready
     uint64_t *empty = bars + 3 * MAX_STAGES;     // [PS] count 1 (tcgen05.commit): planes consumed
     uint64_t *acc_full = bars + 4 * MAX_STAGES;  // count 1
@@ -233,7 +246,10 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     constexpr int CONV_WARPS = CONV_THREADS / 32;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full[s], CONV_THREADS); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < MAX_STAGES; ++s) {
+            mbar_init(&raw_full[s], LOAD_THREADS); mbar_init(&raw_empty[s], CONV_THREADS);
+            mbar_init(&full[s], CONV_THREADS); mbar_init(&empty[s], 1);
+        }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -256,27 +272,27 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
         // Plane byte offset of (j, r) = (j / 8) * 256 + (r / 16) * 128 + (j % 8) * 16 + r % 16.
         const float scale = qp->scale;
         const int total_items = d * (ROWS / 16);                        // (column, 16-row chunk) pairs per stage
-        const bool has_item = (int)threadIdx.x < total_items;           // d = 256: two items per thread would be needed --
-        long long csum = 0;                                             // this layout is only launched for d <= 128
-        const int j = threadIdx.x % d, kc = threadIdx.x / d;
+        const int n_items = (total_items + CONV_THREADS - 1) / CONV_THREADS;
+        long long csum = 0;                                             // all of a thread's items share one column
+        const int j = threadIdx.x % d;
         const int mi = __ldg(m_int + j);
-        float cur[16], nxt[16];
-        auto fetch = [&](int st, float (&v)[16]) {                      // 16 rows of one column: a warp reads 128 contiguous bytes per row
-            const int64_t row0 = r0 + (int64_t)st * ROWS + kc * 16;
-#pragma unroll
-            for (int rr = 0; rr < 16; ++rr) v[rr] = (has_item && row0 + rr < r1) ? __ldg(x + (row0 + rr) * (int64_t)d + j) : 0.f;
-        };
-        if (n_stages > 0) fetch(0, cur);
         for (int st = 0; st < n_stages; ++st) {
-            const int s = st % PS;
-            if (st + 1 < n_stages) fetch(st + 1, nxt);                  // in flight while this stage is converted
+            const int rs = st % RAW_STAGES, s = st % PS;
+            mbar_wait(&raw_full[rs], (st / RAW_STAGES) & 1);
             mbar_wait(&empty[s], ((st / PS) & 1) ^ 1);
+            const unsigned char *raw = sR + rs * raw_bytes;
             unsigned char *base = sP + s * stage_bytes;
-            const int64_t row0 = r0 + (int64_t)st * ROWS + kc * 16;
-            if (has_item) {
+            const int64_t row0 = r0 + (int64_t)st * ROWS;
+            for (int it = 0; it < n_items; ++it) {
+                if ((int)threadIdx.x + it * CONV_THREADS >= total_items) break;   // spare threads only keep the barriers' counts
+                const int kc = (threadIdx.x + it * CONV_THREADS) / d;
                 int qv[16];
 #pragma unroll
-                for (int rr = 0; rr < 16; ++rr) qv[rr] = (row0 + rr < r1) ? __float2int_rn(cur[rr] * scale) - mi : 0;
+                for (int rr = 0; rr < 16; ++rr) {
+                    const int r = kc * 16 + rr;
+                    const float v = *reinterpret_cast<const float *>(raw + r * raw_stride + (((j >> 2) ^ (r & 7)) << 4) + (j & 3) * 4);
+                    qv[rr] = (row0 + r < r1) ? __float2int_rn(v * scale) - mi : 0;
+                }
                 uint4 pl[4];
 #pragma unroll
                 for (int wq = 0; wq < 4; ++wq) {
@@ -299,16 +315,15 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             }
             fence_proxy_async();
             mbar_arrive(&full[s]);
-#pragma unroll
-            for (int rr = 0; rr < 16; ++rr) cur[rr] = nxt[rr];
+            mbar_arrive(&raw_empty[rs]);
         }
-        if (owns_colsum && has_item && csum != 0) atomicAdd(reinterpret_cast<unsigned long long *>(colsum + j), (unsigned long long)csum);
+        if (owns_colsum && csum != 0) atomicAdd(reinterpret_cast<unsigned long long *>(colsum + j), (unsigned long long)csum);
       } else {
-        // ------------------------------------------------------------ converters: f32 (global) -> 4 byte planes
+        // ------------------------------------------------------------ converters: raw f32 (smem) -> 4 byte planes
         // thread -> (row lane rl = tid % 8, column group cg = (tid / 8) % 16, half h = tid / 128); it converts rows
-        // rl + 8*i, i in {2h, 2h+1}, 16 columns each.  A quarter-warp = 8 consecutive rows of one column group = one
-        // 128-byte core matrix on the plane side (conflict-free STS.128); on the global side every lane reads whole
-        // 64-byte pieces (two full sectors) of its rows with 128-bit read-only loads.
+        // rl + 8*i, i in {2h, 2h+1}.  A quarter-warp = 8 consecutive rows of one column group = one 128-byte core matrix
+        // on the plane side (conflict-free STS.128); on the raw side the 16-byte row skew puts the 8 rows in 8 distinct
+        // 16-byte bank slots (conflict-free LDS.128).
         const int rl = threadIdx.x & 7, cs = (threadIdx.x >> 3) & 15, half = threadIdx.x >> 7;
         const bool has_cg = cs < n_cg;
         const int cg = has_cg ? cs : 0;
@@ -319,21 +334,11 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
         long long csum[16];                              // exact column sums of q over this thread's rows
 #pragma unroll
         for (int c = 0; c < 16; ++c) csum[c] = 0;
-        float4 cur[2][4], nxt[2][4];
-        auto fetch = [&](int st, float4 (&v)[2][4]) {
-#pragma unroll
-            for (int ii = 0; ii < 2; ++ii) {
-                const int64_t row = r0 + (int64_t)st * ROWS + rl + 8 * (2 * half + ii);
-                const float4 *xp = reinterpret_cast<const float4 *>(x + row * (int64_t)d + cg * 16);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) v[ii][q] = (has_cg && row < r1) ? __ldg(xp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        if (n_stages > 0) fetch(0, cur);
         for (int st = 0; st < n_stages; ++st) {
-            const int s = st % PS;
-            if (st + 1 < n_stages) fetch(st + 1, nxt);   // in flight while this stage is converted
+            const int rs = st % RAW_STAGES, s = st % PS;
+            mbar_wait(&raw_full[rs], (st / RAW_STAGES) & 1);   // the loaders' cp.async for this stage have landed
             mbar_wait(&empty[s], ((st / PS) & 1) ^ 1);   // the MMAs that read these planes last time have retired
+            const unsigned char *raw = sR + rs * raw_bytes;
             unsigned char *base = sP + s * stage_bytes;
             if (has_cg) {
 #pragma unroll
@@ -342,9 +347,10 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
                     const int64_t row = r0 + (int64_t)st * ROWS + rr;
                     int qv[16];
                     if (row < r1) {
+                        const unsigned char *xrow = raw + rr * raw_stride;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 v = cur[ii][q];
+                            const float4 v = *reinterpret_cast<const float4 *>(xrow + (((cg * 4 + q) ^ (rr & 7)) << 4));
                             qv[4 * q + 0] = __float2int_rn(v.x * scale) - mi[q].x;
                             qv[4 * q + 1] = __float2int_rn(v.y * scale) - mi[q].y;
                             qv[4 * q + 2] = __float2int_rn(v.z * scale) - mi[q].z;
@@ -378,10 +384,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             }
             fence_proxy_async();
             mbar_arrive(&full[s]);
-#pragma unroll
-            for (int ii = 0; ii < 2; ++ii)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) cur[ii][q] = nxt[ii][q];
+            mbar_arrive(&raw_empty[rs]);
         }
         if (owns_colsum && has_cg) {                    // integer atomics: exact and order-independent
 #pragma unroll
@@ -450,6 +453,32 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             __syncwarp();
             if (((st + 1) % DRAIN_STAGES) == 0 || st + 1 == n_stages) ++drains;
         }
+    } else if (warp >= CONV_WARPS + 5) {
+        // ------------------------------------------------------------ loaders: coalesced 16-byte cp.async, 4 stages deep.
+        // (Separate warps on purpose: the converters' fence.proxy.async would otherwise wait for their own in-flight
+        //  prefetches and serialise the ring.)
+        // thread -> fixed 16-byte column piece pc and a fixed row phase; it walks down the stage's rows with constant
+        // strides (no per-piece division: the first version spent ~80 instructions per piece on index arithmetic)
+        const int lt = threadIdx.x - (CONV_WARPS + 5) * 32;            // 0..127
+        const int ppr = d / 4;                                          // 16-byte pieces per row: 32 (d=128) or 64 (d=256)
+        const int pc = lt % ppr, rr0 = lt / ppr, rstep = LOAD_THREADS / ppr;   // rows rr0, rr0+rstep, ...
+        for (int st = 0; st < n_stages; ++st) {
+            const int rs = st % RAW_STAGES;
+            mbar_wait(&raw_empty[rs], ((st / RAW_STAGES) & 1) ^ 1);
+            const int64_t row0 = r0 + (int64_t)st * ROWS;
+            unsigned char *dst = sR + rs * raw_bytes + rr0 * raw_stride;
+            const float *src = x + (row0 + rr0) * (int64_t)d + pc * 4;
+            const int64_t rows_left = r1 - row0;                        // >= 1
+#pragma unroll 4
+            for (int rr = rr0; rr < ROWS; rr += rstep) {
+                const bool in = rr < rows_left;
+                cp_async_cg16(dst + ((pc ^ (rr & 7)) << 4), in ? src : x, in ? 16 : 0);
+                dst += rstep * raw_stride;
+                src += (int64_t)rstep * d;
+            }
+            cp_async_arrive_noinc(&raw_full[rs]);
+        }
+        cp_async_wait_all();
     }
 
     tc_fence_before();
@@ -512,14 +541,14 @@ void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double 
     int64_t slices = std::max<int64_t>(1, std::min<int64_t>(148 / stripes, (n + 4 * ROWS - 1) / (4 * ROWS)));   // one wave
     const int64_t rows_per_slice = ((n + slices - 1) / slices + ROWS - 1) / ROWS * ROWS;
     slices = (n + rows_per_slice - 1) / rows_per_slice;
-    const size_t smem = (size_t)PS * 4 * ROWS * d + (4 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
+    const size_t smem = (size_t)PS * 4 * ROWS * d + (size_t)RAW_STAGES * ROWS * (d * 4) + (4 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
     // plane layout: CLEORA_B200_GRAM_LAYOUT=mn|k overrides the per-shape default (see the kernel's comment)
     static const int forced = [] {
         const char *e = getenv("CLEORA_B200_GRAM_LAYOUT");
         const std::string v = e ? e : "";
         return v == "mn" ? 0 : v == "k" ? 1 : -1;
     }();
-    const bool kmajor = (forced >= 0 ? forced == 1 : d < 256) && d * (ROWS / 16) <= CONV_THREADS;   // K-major: one item per converter
+    const bool kmajor = forced >= 0 ? forced == 1 : d < 256;
     auto kernel = kmajor ? gram_i8_kernel<true> : gram_i8_kernel<false>;
     const int threads = THREADS;
     // per device, not per process: set on every launch (a host-side table write)
