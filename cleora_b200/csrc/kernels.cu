@@ -207,9 +207,11 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const int64_t *__restric
     int64_t row = warp * RPW + lane / LPR;
     bool valid = row < n_rows;
     // Several rows share a warp when the rows are narrow: walk them in degree order (skewed graphs only) so that the
-    // lane groups of a warp finish together -- on a power-law graph the warp otherwise runs as long as its longest row
-    // (measured on the products-shaped graph, 32-float slices: 27.2 ms in index order against 17.6 ms for full rows).
-    if (LPR < 32 && order != nullptr && valid) row = order[row];
+    // lane groups of a warp finish together -- on a power-law graph the warp otherwise runs as long as its longest row.
+    // Measured on the products-shaped graph (ms for the full product, index order -> degree order inside 4096-row
+    // windows; full rows: 17.5): 64-float slices 20.8 -> 16.5, 32-float 27.2 -> 24.1, but 16-float 40.0 -> 60.5 and
+    // 8-float 94 -> 172 (profiles/r2d_, r2g_k1_slices_c3.txt) -- so only the lane-group widths 8 and 16 use it.
+    if (LPR < 32 && LPR >= 8 && order != nullptr && valid) row = order[row];
     int64_t s = 0, e = 0;
     if (valid) { s = rowptr[row]; e = rowptr[row + 1]; }
     if (e - s > long_threshold) {                               // a hub row: the chunked kernels own it
@@ -347,7 +349,7 @@ static void launch_rows(const DeviceGraph &g, const float *val, const float *x, 
     const bool split = g.n_long > 0;
     spmm_rows_kernel<LPR, VEC, U><<<(unsigned)blocks, threads, 0, st>>>(
         g.rowptr, g.col, val, x, out, resid, g.n_rows, alpha, rw, norm, split ? g.long_threshold : INT64_MAX,
-        LPR < 32 ? g.row_order : nullptr, peers);
+        (LPR < 32 && LPR >= 8) ? g.row_order : nullptr, peers);
     LAUNCH_CHECK();
     if (split) {
         float *partial = (float *)workspace().spmm_partials.get((size_t)g.n_long_chunks * LPR * VEC * 4 * sizeof(float));
