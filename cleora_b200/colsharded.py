@@ -40,9 +40,13 @@ SPMM_WIDTHS = (8, 16, 32, 64, 96, 128, 192, 256, 384, 512, 1024)     # kernels.c
 
 
 def eligible(d: int, world: int) -> bool:
-    """Shapes the column-sharded loop covers: an even column split whose slice has a vectorised SpMM kernel."""
-    return (1 < world <= 8 and d % world == 0 and (d // world) in SPMM_WIDTHS and d in SPMM_WIDTHS
-            and os.environ.get("CLEORA_B200_COLSHARD", "1") != "0")
+    """Shapes the column-sharded loop is used for: an even column split whose slice has a vectorised SpMM kernel and is
+    at least 32 floats wide.  Narrower slices work (CLEORA_B200_COLSHARD=force) but gather 64 bytes or less per edge,
+    which HBM serves at about half its bandwidth (ncu, 16-float slices of the products-shaped graph: 54 % of the DRAM
+    peak against 85 % for full rows, profiles/r2l_*), so for d / world < 32 the row-sharded loop is the faster one."""
+    mode = os.environ.get("CLEORA_B200_COLSHARD", "1")
+    ok = 1 < world <= 8 and d % world == 0 and (d // world) in SPMM_WIDTHS and d in SPMM_WIDTHS
+    return ok and mode != "0" and (d // world >= 32 or mode == "force")
 
 
 class CudaPeerBuffer:

@@ -132,9 +132,12 @@ void attach_long_row_schedule(DeviceGraph &d, const std::vector<int64_t> &rowptr
     const int64_t threshold = env_int64("CLEORA_B200_LONG_ROW", 65536), chunk = env_int64("CLEORA_B200_LONG_CHUNK", 4096);
     std::vector<int64_t> rows, cptr{0};
     std::vector<int32_t> owner;
+    const int64_t sched = std::max<int64_t>(1024, threshold / 16);     // narrow-row kernels split sooner (kernels.cu: launch_rows)
+    int64_t max_degree = 0;
     for (int64_t r = 0; r < n_rows; ++r) {
         const int64_t deg = rowptr[(size_t)r + 1] - rowptr[(size_t)r];
-        if (deg > threshold) {
+        max_degree = std::max(max_degree, deg);
+        if (deg > sched) {
             const int64_t nc = (deg + chunk - 1) / chunk;
             for (int64_t c = 0; c < nc; ++c) owner.push_back((int32_t)rows.size());
             rows.push_back(r);
@@ -164,6 +167,8 @@ void attach_long_row_schedule(DeviceGraph &d, const std::vector<int64_t> &rowptr
         }
     }
     dg->long_threshold = threshold;
+    dg->long_sched_threshold = sched;
+    dg->max_degree = max_degree;
     dg->long_chunk_edges = chunk;
     dg->n_long = (int64_t)rows.size();
     dg->n_long_chunks = (int64_t)owner.size();

@@ -24,7 +24,10 @@ struct DeviceGraph {
     uint64_t *hash = nullptr;
     // long-row schedule: rows with more than long_threshold edges are split into chunks of long_chunk_edges, one warp
     // per chunk (kernels.cu); built at upload time
+    // long_threshold applies to full-width rows (32 lanes per row); narrower kernels scale it down to
+    // long_sched_threshold at the least, which is the degree above which a row enters the schedule at all
     int64_t n_long = 0, n_long_chunks = 0, long_threshold = INT64_MAX, long_chunk_edges = 0;
+    int64_t long_sched_threshold = INT64_MAX, max_degree = 0;
     int64_t *long_rows = nullptr;          // [n_long] row indices
     int64_t *long_chunk_ptr = nullptr;     // [n_long + 1] first chunk of each long row
     int32_t *long_chunk_owner = nullptr;   // [n_long_chunks] index into long_rows

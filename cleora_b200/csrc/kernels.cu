@@ -237,17 +237,22 @@ __global__ void __launch_bounds__(256) spmm_long_partial_kernel(const int64_t *_
                                                                 const int64_t *__restrict__ long_rows,
                                                                 const int64_t *__restrict__ chunk_ptr,
                                                                 const int32_t *__restrict__ chunk_owner, int64_t n_chunks,
-                                                                int64_t chunk_edges, float *__restrict__ partial) {
+                                                                int64_t chunk_edges, int64_t long_threshold,
+                                                                float *__restrict__ partial) {
     constexpr int RPW = 32 / LPR, D4 = LPR * VEC;
     const int lane = threadIdx.x & 31, gl = lane & (LPR - 1);
     const int64_t c = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
-    const bool valid = c < n_chunks;
+    bool valid = c < n_chunks;
     int64_t s = 0, e = 0;
     if (valid) {
         const int32_t ri = chunk_owner[c];
         const int64_t row = long_rows[ri];
-        s = rowptr[row] + (c - chunk_ptr[ri]) * chunk_edges;
-        e = min(rowptr[row + 1], s + chunk_edges);
+        if (rowptr[row + 1] - rowptr[row] > long_threshold) {   // the schedule lists every row that is long for SOME width
+            s = rowptr[row] + (c - chunk_ptr[ri]) * chunk_edges;
+            e = min(rowptr[row + 1], s + chunk_edges);
+        } else {
+            valid = false;
+        }
     }
     float4 acc[VEC];
 #pragma unroll
@@ -261,15 +266,18 @@ __global__ void __launch_bounds__(256) spmm_long_partial_kernel(const int64_t *_
 }
 
 template <int LPR, int VEC>
-__global__ void __launch_bounds__(256) spmm_long_finish_kernel(const int64_t *__restrict__ long_rows,
+__global__ void __launch_bounds__(256) spmm_long_finish_kernel(const int64_t *__restrict__ rowptr,
+                                                               const int64_t *__restrict__ long_rows,
                                                                const int64_t *__restrict__ chunk_ptr, int64_t n_long,
+                                                               int64_t long_threshold,
                                                                const float *__restrict__ partial, float *__restrict__ out,
                                                                const float *__restrict__ resid, float alpha, float rw,
                                                                int norm, PeerOut peers) {
     constexpr int RPW = 32 / LPR, D4 = LPR * VEC;
     const int lane = threadIdx.x & 31, gl = lane & (LPR - 1);
     const int64_t ri = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
-    const bool valid = ri < n_long;
+    bool valid = ri < n_long;
+    if (valid) { const int64_t row = long_rows[ri]; valid = rowptr[row + 1] - rowptr[row] > long_threshold; }
     float4 acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -346,19 +354,25 @@ static void launch_rows(const DeviceGraph &g, const float *val, const float *x, 
     const int threads = 256;
     const int64_t rows_per_block = (int64_t)(threads / 32) * RPW;
     const int64_t blocks = (g.n_rows + rows_per_block - 1) / rows_per_block;
-    const bool split = g.n_long > 0;
+    // A row is walked sequentially by ONE lane group, LPR edges per memory round trip: the time of the longest row is a
+    // floor for the launch, and with narrow rows (few lanes per row) that floor is reached 32/LPR times sooner --
+    // measured on the products-shaped graph, 25k-edge hubs: 2.5 ms per launch at 4 lanes per row against 1.3 ms for
+    // all other rows together.  So the splitting threshold scales with the lane-group width (full-width rows keep the
+    // configured value and with it their bit-exact sequential sums up to that degree).
+    const int64_t thr = std::max<int64_t>(g.long_sched_threshold, g.long_threshold / 32 * LPR);
+    const bool split = g.n_long > 0 && thr < g.max_degree;
     spmm_rows_kernel<LPR, VEC, U><<<(unsigned)blocks, threads, 0, st>>>(
-        g.rowptr, g.col, val, x, out, resid, g.n_rows, alpha, rw, norm, split ? g.long_threshold : INT64_MAX,
+        g.rowptr, g.col, val, x, out, resid, g.n_rows, alpha, rw, norm, split ? thr : INT64_MAX,
         (LPR < 32 && LPR >= 8) ? g.row_order : nullptr, peers);
     LAUNCH_CHECK();
     if (split) {
         float *partial = (float *)workspace().spmm_partials.get((size_t)g.n_long_chunks * LPR * VEC * 4 * sizeof(float));
         spmm_long_partial_kernel<LPR, VEC, U><<<(unsigned)((g.n_long_chunks + rows_per_block - 1) / rows_per_block), threads, 0, st>>>(
             g.rowptr, g.col, val, x, g.long_rows, g.long_chunk_ptr, g.long_chunk_owner, g.n_long_chunks,
-            g.long_chunk_edges, partial);
+            g.long_chunk_edges, thr, partial);
         LAUNCH_CHECK();
         spmm_long_finish_kernel<LPR, VEC><<<(unsigned)((g.n_long + rows_per_block - 1) / rows_per_block), threads, 0, st>>>(
-            g.long_rows, g.long_chunk_ptr, g.n_long, partial, out, resid, alpha, rw, norm, peers);
+            g.rowptr, g.long_rows, g.long_chunk_ptr, g.n_long, thr, partial, out, resid, alpha, rw, norm, peers);
         LAUNCH_CHECK();
     }
 }

@@ -154,7 +154,7 @@ def _free_port():
 
 
 def _worker(rank, world, port, case, ret):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), CLEORA_B200_COLSHARD="force")   # small d in these tests
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         lines, columns, kw = case
@@ -208,8 +208,12 @@ def run_cols(world, case):
 ER = (er_lines(601, 4000, 3), "complex::reflexive::node")          # 601 rows: the last row block is shorter
 
 
-def test_eligibility():
-    assert colsharded.eligible(256, 8) and colsharded.eligible(128, 8) and colsharded.eligible(256, 2)
+def test_eligibility(monkeypatch):
+    assert colsharded.eligible(256, 8) and colsharded.eligible(128, 4) and colsharded.eligible(256, 2)
+    assert not colsharded.eligible(128, 8)                  # 16-float slices: row-sharded is faster (HBM granularity)
+    monkeypatch.setenv("CLEORA_B200_COLSHARD", "force")
+    assert colsharded.eligible(128, 8) and colsharded.eligible(32, 4)
+    monkeypatch.delenv("CLEORA_B200_COLSHARD")
     assert not colsharded.eligible(256, 1) and not colsharded.eligible(48, 4) and not colsharded.eligible(100, 2)
     assert not colsharded.eligible(64, 3)
 
