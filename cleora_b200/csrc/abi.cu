@@ -471,13 +471,13 @@ enum { PH_H2D = 0, PH_INIT, PH_SPMM, PH_STATS, PH_EIGH, PH_APPLY, PH_RMSE, PH_D2
 // `cholesky`: use T = L^-T (chol_whiten.cu) instead of the PCA transform -- only for iterates that are never handed
 // to the caller (see embed_reference_order); dout must equal d then.
 void whiten_device(const float *Y, int64_t n, int64_t d, int64_t dout, float *Z, WhitenState &ws, cudaStream_t st,
-                   Phase &ph, bool cholesky = false) {
+                   Phase &ph, bool cholesky = false, bool ieee_f64 = false) {
     ws.ensure(d, dout);
     ph.begin();
     AbsmaxPartials mx;
     launch_col_sums(Y, n, d, ws.sums.p, false, st, &mx);
     launch_scale_f64(ws.sums.p, d, 1.0 / (double)n, st);                 // mean (f64)
-    launch_centered_gram(Y, n, d, ws.sums.p, ws.cov.p, st, &mx);
+    launch_centered_gram(Y, n, d, ws.sums.p, ws.cov.p, st, &mx, ieee_f64);
     launch_scale_f64(ws.cov.p, d * d, 1.0 / (double)(n - 1), st);        // cov *= 1/(n-1)
     launch_f64_to_f32(ws.sums.p, ws.mean32.p, d, st);                    // mean.astype(float32)
     ph.end(PH_STATS);
@@ -1210,7 +1210,7 @@ extern "C" int cleora_whiten_embeddings(const float *x, int64_t n, int64_t d, in
         CUDA_TRY(cudaMemcpy(dx.p, x, dx.n * sizeof(float), cudaMemcpyHostToDevice));
         WhitenState &ws = persistent().ws;
         Phase ph;
-        whiten_device(dx.p, n, d, dout, dz.p, ws, nullptr, ph);
+        whiten_device(dx.p, n, d, dout, dz.p, ws, nullptr, ph, false, true);      // arbitrary user data: IEEE f64 covariance
         CUDA_TRY(cudaMemcpy(out, dz.p, dz.n * sizeof(float), cudaMemcpyDeviceToHost));
         ws.eig.check_info();
     });

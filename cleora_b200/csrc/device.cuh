@@ -119,8 +119,11 @@ struct AbsmaxPartials {
 };
 void launch_col_sums(const float *x, int64_t n, int64_t d, double *sums, bool accumulate, cudaStream_t st,
                      AbsmaxPartials *absmax = nullptr);
+// ieee_f64: always the FP64 DMMA kernel.  The integer tensor-core path quantises with ONE global step (max|x| 2^-30):
+// exact for the loop's row-normalised iterates, but a user matrix whose columns differ in scale by ~1e8 would lose its
+// small columns -- the stand-alone whiten_embeddings entry point therefore asks for IEEE f64.
 void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st,
-                          const AbsmaxPartials *absmax = nullptr);
+                          const AbsmaxPartials *absmax = nullptr, bool ieee_f64 = false);
 void launch_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
                          float *out, cudaStream_t st);
 bool whiten_apply_tc_supported(int64_t d, int64_t dout);

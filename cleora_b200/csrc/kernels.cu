@@ -824,11 +824,11 @@ void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double 
                              const AbsmaxPartials *absmax);
 
 void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st,
-                          const AbsmaxPartials *absmax) {
+                          const AbsmaxPartials *absmax, bool ieee_f64) {
     if (d == 0) return;
     {   // exact-integer tcgen05 path for the large, common shapes; CLEORA_B200_GRAM=v3|v2 forces the FP64 DMMA kernels
         static const bool allow_i8 = [] { const char *e = getenv("CLEORA_B200_GRAM"); return !e || std::string(e) == "i8"; }();
-        if (allow_i8 && gram_i8_supported(n, d) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        if (allow_i8 && !ieee_f64 && gram_i8_supported(n, d) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
             launch_centered_gram_i8(x, n, d, mean, cov, st, absmax);
             return;
         }
