@@ -14,11 +14,11 @@ import numpy as np
 
 from . import _lib
 from ._lib import check, ptr
-from .pycleora import SparseMatrix
+from .pycleora import SparseMatrix, get_devices, set_devices
 
 __all__ = ["SparseMatrix", "embed", "whiten_embeddings", "embed_using_baseline_cleora", "embed_multiscale",
            "embed_with_node_features", "embed_inductive", "update_graph", "pinned_empty", "set_option", "synth_pairs",
-           "release_workspace", "DEFAULT_FEATURE_DIM", "DEFAULT_NUM_ITERATIONS"]
+           "release_workspace", "set_devices", "get_devices", "DEFAULT_FEATURE_DIM", "DEFAULT_NUM_ITERATIONS"]
 
 DEFAULT_FEATURE_DIM = 256          # pycleora/__init__.py:12
 DEFAULT_NUM_ITERATIONS = 40        # pycleora/__init__.py:13

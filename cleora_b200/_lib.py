@@ -74,6 +74,9 @@ PROTOTYPES = {
     "cleora_spectral_rotate": (C.c_int, [c_f32p, C.c_int64, C.c_int64, c_f32p]),
     "cleora_embed": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_double,
                                C.c_int, C.c_int, c_f32p, c_i64p, c_f64p]),
+    "cleora_embed_multi": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, c_f32p, C.c_int64, C.c_int64, C.c_int,
+                                     C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, c_f32p, c_i64p]),
+    "cleora_embed_multi_supported": (C.c_int, [C.c_int64, C.c_int]),
     "cleora_set_eigh": (None, [EIGH_FN, C.c_void_p]),
     "cleora_set_eigh_thread": (None, [C.c_int, EIGH_FN, C.c_void_p]),
     "cleora_set_option": (C.c_int, [C.c_char_p, C.c_int64]),

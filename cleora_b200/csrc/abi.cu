@@ -7,13 +7,16 @@
 #include <cusolverDn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
 struct cleora_graph : cleora::Graph {};
@@ -675,6 +678,8 @@ void embed_pipelined(DeviceGraph &dg, const float *val, int markov, float *cur, 
     *result = cur;
 }
 
+#include "multi_gpu.inl"
+
 }  // namespace
 }  // namespace cleora
 
@@ -702,6 +707,10 @@ extern "C" int cleora_set_option(const char *key, int64_t value) {
         const std::string k = key ? key : "";
         if (k == "pipeline_whiten") g_opt_pipeline.store(value != 0);
         else if (k == "chol_whiten") g_opt_chol.store(value != 0);
+        else if (k == "k3_bk") {
+            if (value != 16 && value != 32) value_error("k3_bk must be 16 or 32");
+            g_k3_bk.store((int)value);
+        }
         else value_error("unknown option '" + k + "'");
     });
 }
@@ -709,6 +718,7 @@ extern "C" int64_t cleora_get_option(const char *key) {
     const std::string k = key ? key : "";
     if (k == "pipeline_whiten") return g_opt_pipeline.load();
     if (k == "chol_whiten") return g_opt_chol.load();
+    if (k == "k3_bk") return g_k3_bk.load();
     return -1;
 }
 extern "C" int cleora_host_alloc(size_t nbytes, void **out) {
@@ -1339,3 +1349,24 @@ extern "C" int cleora_embed(cleora_graph_t *g, const float *x0, int64_t d, int64
         if (iters_done) *iters_done = done;
     });
 }
+
+// embed() on several GPUs of this box from ONE process and ONE call (multi_gpu.inl): the column-sharded loop with peer
+// stores over NVLink, host threads instead of ranks, events instead of NCCL.  normalization == CLEORA_NORM_L2_RUST selects
+// the Rust fast path's semantics (embed_full[_with_convergence], src/embedding.rs:106-188) as cleora_embed_fast does.
+extern "C" int cleora_embed_multi(cleora_graph_t *g, const int *devices, int n_devices, const float *x0, int64_t d,
+                                  int64_t iters, int markov, int64_t seed, double residual_weight,
+                                  double convergence_threshold, int normalization, int whiten, float *out,
+                                  int64_t *iters_done) {
+    return guarded([&] {
+        if (!devices || n_devices < 1) value_error("at least one device is required");
+        MultiArgs a{};
+        a.g = g; a.x0 = x0; a.d = d; a.iters = iters; a.seed = seed;
+        a.markov = markov; a.norm = normalization; a.whiten = whiten;
+        a.rust = normalization == CLEORA_NORM_L2_RUST ? 1 : 0;
+        a.residual_weight = residual_weight; a.convergence_threshold = convergence_threshold;
+        a.out = out;
+        a.eigh = current_eigh();
+        embed_multi(a, devices, n_devices, iters_done);
+    });
+}
+extern "C" int cleora_embed_multi_supported(int64_t d, int n_devices) { return multi_eligible(d, n_devices) ? 1 : 0; }

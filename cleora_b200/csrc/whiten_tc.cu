@@ -25,16 +25,21 @@
 #include "../../include/cleora_b200.h"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <type_traits>
 
 namespace cleora {
 
 namespace tc {
 
 constexpr int BM = 128;            // rows per tile (UMMA M)
-constexpr int BK = 32;             // K per stage (floats) = 128 bytes per row
-constexpr int STAGES = 2;
+// K per stage (floats) and pipeline depth are template parameters of the kernel: (32, 2) = round 1's shape, (16, 4) = the
+// same bytes in flight cut into twice as many stages.  With two stages the refill of a stage (L2 latency + 64 KB of
+// transform) can only start when the MMAs that read it retire and must finish within ONE stage time; with four half-size
+// stages it has three stage times.
+constexpr int BK_MAX = 32;
 constexpr int NMAX = 256;          // UMMA N limit
-constexpr int A_BYTES = BM * BK * 4;            // 16 KB (one of hi / lo)
 constexpr int B_LOAD_THREADS = 64;  // 2 loader warps for the transform
 constexpr int THREADS = 288 + B_LOAD_THREADS;
 constexpr int EPI_LD = 36;          // floats per row of an epilogue staging tile (32 + 4: conflict-free 128-bit rows)
@@ -134,18 +139,18 @@ __device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__flo
 }  // namespace tc
 
 // Pre-split and pre-tile the transform for the tensor-core kernel.  For every K chunk c (32 rows of T) the image
-// is exactly what the UMMA descriptor expects for a K-major B operand [N x 32]: element (n, k) of the chunk at
-// byte (n%8)*16 + (k%4)*4 + (k/4)*128 + (n/8)*1024.  Bt = [chunk][hi|lo][N*32 floats].
-__global__ void prep_transform_kernel(const float *__restrict__ T, int d, int dout, float *__restrict__ Bt) {
+// is exactly what the UMMA descriptor expects for a K-major B operand [N x BK]: element (n, k) of the chunk at
+// byte (n%8)*16 + (k%4)*4 + (k/4)*128 + (n/8)*(BK*32).  Bt = [chunk][hi|lo][N*BK floats].
+__global__ void prep_transform_kernel(const float *__restrict__ T, int d, int dout, int BK, float *__restrict__ Bt) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)d * dout) return;
     const int k = (int)(idx / dout), n = (int)(idx - (int64_t)k * dout);
-    const int c = k / tc::BK, kk = k % tc::BK;
+    const int c = k / BK, kk = k % BK;
     const float v = T[idx];
     const float hi = tc::tf32_hi(v);
     const float lo = v - hi;
-    const int64_t chunk_floats = (int64_t)dout * tc::BK;
-    const int64_t off = (int64_t)(n % 8) * 4 + (kk % 4) + (int64_t)(kk / 4) * 32 + (int64_t)(n / 8) * 256;
+    const int64_t chunk_floats = (int64_t)dout * BK;
+    const int64_t off = (int64_t)(n % 8) * 4 + (kk % 4) + (int64_t)(kk / 4) * 32 + (int64_t)(n / 8) * (BK * 8);
     float *base = Bt + (int64_t)c * 2 * chunk_floats;
     base[off] = hi;
     base[chunk_floats + off] = lo;
@@ -154,12 +159,15 @@ __global__ void prep_transform_kernel(const float *__restrict__ T, int d, int do
 // NORM: 0 none, 2 row L2 (x / max(norm, 1e-10)) fused into the epilogue.
 // SCALED: 0 -> a = x - mean;  1 -> a = x - rowscale[r] * mean  (x = A*Y with A not yet applied to the centring:
 //         A (Y - 1 mean^T) = A Y - (A 1) mean^T, rowscale = A 1; used by the pipelined loop, see abi.cu).
-template <int NORM, int SCALED>
+template <int NORM, int SCALED, int BK, int STAGES>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const float *__restrict__ mean,
                        const float *__restrict__ rowscale, const float *__restrict__ Bt, int NT, int upper,
                        float *__restrict__ out, PeerOut peers) {
     using namespace tc;
+    constexpr int A_BYTES = BM * BK * 4;                             // one of hi / lo: 16 KB (BK = 32) or 8 KB (BK = 16)
+    constexpr int SBO = BK * 32;                                     // bytes between 8-row groups of an operand tile
+    constexpr int Q = BK / 4;                                        // float4 per row and stage
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int halves = NT > NMAX ? 2 : 1;                            // column halves of a row tile (two accumulator passes)
     const int N = NT / halves;                                       // UMMA N
@@ -214,13 +222,13 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
                 if (++p == per_tile) { p = 0; t += gridDim.x; }
             } while (first_col(p / n_chunks, p % n_chunks) >= N);
         };
-        float4 cur[8], nxt[8];
-        auto fetch = [&](int64_t tile, int c, float4 (&v)[8]) {
+        float4 cur[Q], nxt[Q];
+        auto fetch = [&](int64_t tile, int c, float4 (&v)[Q]) {
             const int64_t row = tile * BM + r;
             const bool in = row < n;
             const float4 *xr = reinterpret_cast<const float4 *>(x + (in ? row : 0) * (int64_t)d);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = in ? __ldg(xr + c * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < Q; ++q) v[q] = in ? __ldg(xr + c * Q + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         int64_t tile = blockIdx.x;
         int pos = 0;                                    // position inside the tile's (half, chunk) sequence
@@ -239,9 +247,9 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
             const float4 *mp = reinterpret_cast<const float4 *>(mean + c * BK);
             mbar_wait(&empty[s], ph ^ 1);              // stage free (first round passes immediately)
             unsigned char *hi = sA + s * 2 * A_BYTES, *lo = hi + A_BYTES;
-            const int off = (r & 7) * 16 + (r >> 3) * 1024;
+            const int off = (r & 7) * 16 + (r >> 3) * SBO;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < Q; ++q) {
                 float4 m = __ldg(mp + q);
                 if (SCALED) { m.x = __fmul_rn(rs, m.x); m.y = __fmul_rn(rs, m.y); m.z = __fmul_rn(rs, m.z); m.w = __fmul_rn(rs, m.w); }
                 float4 a, hh, l;
@@ -255,7 +263,7 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
             fence_proxy_async();                       // generic-proxy smem writes -> visible to the tensor core
             mbar_arrive(&full_a[s]);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+            for (int q = 0; q < Q; ++q) cur[q] = nxt[q];
             tile = ntile;
             pos = npos;
         }
@@ -355,13 +363,13 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_hi = smem_u32(sA + s * 2 * A_BYTES), a_lo = a_hi + A_BYTES;
-                        const uint32_t b_hi = smem_u32(sB + s * 2 * b_bytes) + (uint32_t)(n0 / 8) * 1024u, b_lo = b_hi + b_bytes;
+                        const uint32_t b_hi = smem_u32(sB + s * 2 * b_bytes) + (uint32_t)(n0 / 8) * (uint32_t)SBO, b_lo = b_hi + b_bytes;
                         const uint32_t tmem_c = tmem_d + (uint32_t)n0;
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k) {                 // UMMA K = 8 tf32 = two 16-byte core columns
                             const uint32_t ko = k * 256;
-                            const uint64_t dah = make_desc(a_hi + ko, 128, 1024), dal = make_desc(a_lo + ko, 128, 1024);
-                            const uint64_t dbh = make_desc(b_hi + ko, 128, 1024), dbl = make_desc(b_lo + ko, 128, 1024);
+                            const uint64_t dah = make_desc(a_hi + ko, 128, SBO), dal = make_desc(a_lo + ko, 128, SBO);
+                            const uint64_t dbh = make_desc(b_hi + ko, 128, SBO), dbl = make_desc(b_lo + ko, 128, SBO);
                             mma_tf32(tmem_c, dal, dbh, idesc_c, (c | k) != 0);   // small terms first
                             mma_tf32(tmem_c, dah, dbl, idesc_c, 1);
                             mma_tf32(tmem_c, dah, dbh, idesc_c, 1);
@@ -389,9 +397,9 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
                 ++it;
                 mbar_wait(&empty[s], ph ^ 1);
                 unsigned char *dst = sB + s * 2 * b_bytes;
-                // rows [h*N, (h+1)*N) of the chunk: 8-row groups are 1024 bytes apart in the image; rows below n0 are zero
+                // rows [h*N, (h+1)*N) of the chunk: 8-row groups are SBO bytes apart in the image; rows below n0 are zero
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(Bt + (int64_t)c * 2 * plane_floats) + (size_t)h * b_bytes;
-                for (int p = lt + (n0 / 8) * 64; p < plane_pieces; p += B_LOAD_THREADS) {
+                for (int p = lt + (n0 / 8) * (SBO / 16); p < plane_pieces; p += B_LOAD_THREADS) {
                     cp_async_cg16(dst + p * 16, src + p * 16);                                            // hi
                     cp_async_cg16(dst + b_bytes + p * 16, src + plane_floats * 4 + p * 16);                // lo
                 }
@@ -409,8 +417,15 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
     }
 }
 
+// Stage shape of K3: 32 = (BK 32, 2 stages), 16 = (BK 16, 4 stages).  cleora_set_option("k3_bk", ...) or CLEORA_B200_K3_BK.
+std::atomic<int> g_k3_bk{[] {
+    const char *e = getenv("CLEORA_B200_K3_BK");
+    const int v = e ? atoi(e) : 0;
+    return (v == 16 || v == 32) ? v : 32;
+}()};
+
 bool whiten_apply_tc_supported(int64_t d, int64_t dout) {
-    if (d % tc::BK != 0 || d < tc::BK || dout < 16) return false;
+    if (d % tc::BK_MAX != 0 || d < tc::BK_MAX || dout < 16) return false;
     if (dout <= tc::NMAX) return dout % 32 == 0;                    // the epilogue moves 32-column blocks
     return dout <= 2 * tc::NMAX && dout % 64 == 0;                  // two halves of <= 256 columns each
 }
@@ -428,10 +443,12 @@ void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *m
     if (peers.mode == PEER_OWNERS) throw CudaFail{"tensor-core apply: unsupported destination mode"};
     float *Bt = (float *)workspace().misc.get((size_t)2 * d * dout * sizeof(float));
     const int64_t tot = d * dout;
-    prep_transform_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(T, (int)d, (int)dout, Bt);
+    const int bk = g_k3_bk.load(), stages = bk == 16 ? 4 : 2;
+    prep_transform_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(T, (int)d, (int)dout, bk, Bt);
     LAUNCH_CHECK();
     const int NT = (int)dout, N = NT > NMAX ? NT / 2 : NT;
-    const size_t smem = (size_t)STAGES * 2 * A_BYTES + (size_t)STAGES * 2 * N * BK * 4 + EPI_BYTES + 16 * sizeof(uint64_t) + 16;
+    const size_t smem = (size_t)stages * 2 * (BM * bk * 4) + (size_t)stages * 2 * N * bk * 4 + EPI_BYTES +
+                        (3 * stages + 4) * sizeof(uint64_t) + 16;
     const int64_t n_tiles = (n + BM - 1) / BM;
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
     auto launch = [&](auto kernel) {
@@ -440,8 +457,14 @@ void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *m
     };
     const bool l2 = norm == CLEORA_NORM_L2_NUMPY;
     if (norm != CLEORA_NORM_NONE && !l2) throw CudaFail{"tensor-core apply: unsupported fused normalisation"};
-    if (rowscale) { if (l2) launch(whiten_apply_tc_kernel<CLEORA_NORM_L2_NUMPY, 1>); else launch(whiten_apply_tc_kernel<0, 1>); }
-    else          { if (l2) launch(whiten_apply_tc_kernel<CLEORA_NORM_L2_NUMPY, 0>); else launch(whiten_apply_tc_kernel<0, 0>); }
+    auto pick = [&](auto norm_c, auto scaled_c) {
+        constexpr int NORM = decltype(norm_c)::value, SCALED = decltype(scaled_c)::value;
+        if (bk == 16) launch(whiten_apply_tc_kernel<NORM, SCALED, 16, 4>);
+        else launch(whiten_apply_tc_kernel<NORM, SCALED, 32, 2>);
+    };
+    using std::integral_constant;
+    if (rowscale) { if (l2) pick(integral_constant<int, CLEORA_NORM_L2_NUMPY>{}, integral_constant<int, 1>{}); else pick(integral_constant<int, 0>{}, integral_constant<int, 1>{}); }
+    else          { if (l2) pick(integral_constant<int, CLEORA_NORM_L2_NUMPY>{}, integral_constant<int, 0>{}); else pick(integral_constant<int, 0>{}, integral_constant<int, 0>{}); }
     LAUNCH_CHECK();
 }
 

@@ -16,6 +16,34 @@ from . import _lib
 from ._lib import check, ptr
 
 
+_DEVICES: List[int] = []
+
+
+def set_devices(devices: Optional[Iterable[int]]) -> None:
+    """GPUs that ``embed()`` / ``embed_fast*()`` / ``embed_device()`` spread one call over, from this one process
+    (include/cleora_b200.h: cleora_embed_multi -- column-sharded SpMM, peer stores over NVLink, no torchrun).  ``None``
+    or a single device restores the one-GPU path; the environment variable CLEORA_B200_DEVICES="0,1,2,3" sets the
+    initial list.  Shapes the multi-GPU loop has no slice kernels for (``d % len(devices) != 0`` ...) run on one GPU."""
+    global _DEVICES
+    _DEVICES = [int(v) for v in devices] if devices is not None else []
+
+
+def get_devices() -> List[int]:
+    return list(_DEVICES)
+
+
+def _multi_devices(d: int):
+    """ctypes int array of the configured devices if this feature dimension can be column-sharded over them."""
+    if len(_DEVICES) < 2 or not _lib.lib().cleora_embed_multi_supported(int(d), len(_DEVICES)):
+        return None
+    return (C.c_int * len(_DEVICES))(*_DEVICES)
+
+
+import os as _os  # noqa: E402
+if _os.environ.get("CLEORA_B200_DEVICES"):
+    set_devices(int(v) for v in _os.environ["CLEORA_B200_DEVICES"].split(",") if v.strip())
+
+
 def _as_matrix(x, name="x") -> np.ndarray:
     """pyo3 accepts only a float32 ndarray with ndim == 2 (`&PyArray2<f32>`); anything else is a TypeError."""
     if not isinstance(x, np.ndarray) or x.dtype != np.float32 or x.ndim != 2:
@@ -300,6 +328,12 @@ class SparseMatrix:
         """src/lib.rs:320-364: init + T x (SpMM -> residual -> L2) with X resident in HBM."""
         m = self._markov_code(propagation)
         out = np.empty((self.num_entities, int(feature_dim)), np.float32)
+        devs = _multi_devices(int(feature_dim))
+        if devs is not None:
+            check(_lib.lib().cleora_embed_multi(self._handle(), devs, len(devs), None, int(feature_dim), int(num_iterations), m,
+                                                int(seed), float(np.float32(residual_weight)), 0.0, _lib.NORM_L2_RUST, 0,
+                                                ptr(out, _lib.c_f32p), None))
+            return out
         check(_lib.lib().cleora_embed_fast(self._handle(), int(feature_dim), int(num_iterations), m, int(seed),
                                            float(residual_weight), ptr(out, _lib.c_f32p)))
         return out
@@ -311,6 +345,13 @@ class SparseMatrix:
         m = self._markov_code(propagation)
         out = np.empty((self.num_entities, int(feature_dim)), np.float32)
         done = C.c_int64(0)
+        devs = _multi_devices(int(feature_dim))
+        if devs is not None:
+            check(_lib.lib().cleora_embed_multi(self._handle(), devs, len(devs), None, int(feature_dim), int(max_iterations), m,
+                                                int(seed), float(np.float32(residual_weight)),
+                                                float(np.float32(convergence_threshold)), _lib.NORM_L2_RUST, 0,
+                                                ptr(out, _lib.c_f32p), C.byref(done)))
+            return out, int(done.value)
         check(_lib.lib().cleora_embed_fast_convergence(self._handle(), int(feature_dim), int(max_iterations), m,
                                                        int(seed), float(residual_weight),
                                                        float(convergence_threshold), ptr(out, _lib.c_f32p),
@@ -349,6 +390,14 @@ class SparseMatrix:
         done = C.c_int64(0)
         host = _lib.auto_host_eigh(self.num_entities, d, int(num_iterations), int(normalization), bool(whiten),
                                    float(residual_weight), float(convergence_threshold))
+        devs = _multi_devices(d) if timings is None else None
+        if devs is not None:
+            with _lib.host_eigh(host):
+                check(_lib.lib().cleora_embed_multi(self._handle(), devs, len(devs), None if x0 is None else ptr(x0, _lib.c_f32p),
+                                                    d, int(num_iterations), m, int(seed), float(residual_weight),
+                                                    float(convergence_threshold), int(normalization), 1 if whiten else 0,
+                                                    ptr(out, _lib.c_f32p), C.byref(done)))
+            return out, int(done.value)
         with _lib.host_eigh(host):
             check(_lib.lib().cleora_embed(self._handle(), None if x0 is None else ptr(x0, _lib.c_f32p), d,
                                           int(num_iterations), m, int(seed), float(residual_weight),

@@ -192,7 +192,9 @@ void cleora_set_eigh_thread(int mode, cleora_eigh_fn fn, void *user);
  *   of the PCA transform of pycleora/__init__.py:145-156; the loop body is equivariant under orthogonal
  *   right-multiplication, so the final iterate (always PCA-whitened) is the reference's.  Falls back to the
  *   eigensolver for the whole call when a covariance is not safely positive definite (lambda_min near the reference's
- *   1e-10 clamp).  0 = eigensolver in every iteration. */
+ *   1e-10 clamp).  0 = eigensolver in every iteration.
+ * "k3_bk" (32 or 16): stage shape of the tensor-core apply kernel -- 32 floats of K per stage, 2 stages, or 16 floats and
+ *   4 stages (same shared memory, refills overlap three stage times instead of one); results are identical. */
 int cleora_set_option(const char *key, int64_t value);
 int64_t cleora_get_option(const char *key);      /* -1 for an unknown key */
 
@@ -242,6 +244,21 @@ int cleora_dev_whiten_apply_slices(const float *x, int64_t n, int64_t d, const f
                                    int normalization, const float *rowscale, int t_upper, void *stream);
 int cleora_dev_normalize_slices(const float *x, int64_t n, int64_t d, int normalization, float *out,
                                 float *const *dests, int n_dst, int64_t row_base, void *stream);
+/* embed() on several GPUs of one box from ONE process and ONE call -- what SURVEY.md section 8(b)/(e) sketched as "devices
+ * inside the handle": the binding passes a device list instead of launching one process per GPU.  Replaces the same
+ * reference entry points as cleora_embed / cleora_embed_fast[_convergence] (pycleora/__init__.py:51-127,
+ * src/lib.rs:320-412), with the same arguments, results and error behaviour; `normalization` = CLEORA_NORM_L2_RUST
+ * selects the Rust fast path's semantics (no whitening, f32 rmse early stop), any other code the Python loop's.
+ * Implementation (cleora_b200/csrc/multi_gpu.inl): the column-sharded loop above with one host thread per entry of
+ * `devices` (entries may repeat: several ranks on one GPU), peer access instead of CUDA IPC, cross-stream events instead
+ * of NCCL barriers, and the two small all-reduces done by every rank itself with peer loads in rank order (bit-identical
+ * statistics on every GPU).  `x0` NULL (deterministic init) or host/device [n, d]; `out` host or device [n, d].
+ * Needs d % n_devices == 0 with both d and d / n_devices in {8, 16, 32, 64, 96, 128, 192, 256, 384, 512, 1024}
+ * (cleora_embed_multi_supported), every device visible and peer-accessible; otherwise CLEORA_ERR_VALUE / _CUDA. */
+int cleora_embed_multi(cleora_graph_t *g, const int *devices, int n_devices, const float *x0, int64_t d, int64_t iters,
+                       int markov, int64_t seed, double residual_weight, double convergence_threshold, int normalization,
+                       int whiten, float *out, int64_t *iters_done);
+int cleora_embed_multi_supported(int64_t d, int n_devices);
 /* Device memory that can be exported to the other ranks of the node (cudaMalloc + cudaIpc*); handles are 64 bytes. */
 int cleora_dev_malloc(size_t nbytes, void **out);
 int cleora_dev_free(void *p);

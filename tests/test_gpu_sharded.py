@@ -112,7 +112,7 @@ def _check(outs):
                 assert gram_err(out, other) <= 1e-5, (kw, name)
 
 
-@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_sharded_ranks_sharing_one_gpu(world):
     _check(_run(world, "gloo"))
 
