@@ -707,6 +707,7 @@ extern "C" int cleora_set_option(const char *key, int64_t value) {
         const std::string k = key ? key : "";
         if (k == "pipeline_whiten") g_opt_pipeline.store(value != 0);
         else if (k == "chol_whiten") g_opt_chol.store(value != 0);
+        else if (k == "k3_asw") g_k3_asw.store(value != 0);
         else if (k == "k3_bk") {
             if (value != 16 && value != 32) value_error("k3_bk must be 16 or 32");
             g_k3_bk.store((int)value);
@@ -719,6 +720,7 @@ extern "C" int64_t cleora_get_option(const char *key) {
     if (k == "pipeline_whiten") return g_opt_pipeline.load();
     if (k == "chol_whiten") return g_opt_chol.load();
     if (k == "k3_bk") return g_k3_bk.load();
+    if (k == "k3_asw") return g_k3_asw.load();
     return -1;
 }
 extern "C" int cleora_host_alloc(size_t nbytes, void **out) {

@@ -127,6 +127,7 @@ void launch_centered_gram(const float *x, int64_t n, int64_t d, const double *me
 void launch_whiten_apply(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,
                          float *out, cudaStream_t st);
 bool whiten_apply_tc_supported(int64_t d, int64_t dout);
+extern std::atomic<int> g_k3_asw;      // K3 A-tile layout: 0 = no swizzle (thread per row), 1 = SWIZZLE_128B (coalesced producers)
 extern std::atomic<int> g_k3_bk;       // K3 stage shape: 32 = (BK 32, 2 stages), 16 = (BK 16, 4 stages); whiten_tc.cu
 // upper_triangular: T has no entries below the diagonal (the Cholesky whitening transform) -- lets K3 skip the zero blocks
 void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *mean_f32, const float *T, int64_t dout,

@@ -159,7 +159,13 @@ __global__ void prep_transform_kernel(const float *__restrict__ T, int d, int do
 // NORM: 0 none, 2 row L2 (x / max(norm, 1e-10)) fused into the epilogue.
 // SCALED: 0 -> a = x - mean;  1 -> a = x - rowscale[r] * mean  (x = A*Y with A not yet applied to the centring:
 //         A (Y - 1 mean^T) = A Y - (A 1) mean^T, rowscale = A 1; used by the pipelined loop, see abi.cu).
-template <int NORM, int SCALED, int BK, int STAGES>
+// ASW: 0 -> A tiles in the no-swizzle canonical layout, produced by one thread per row (each warp load instruction
+//           touches 32 different 128-byte lines);
+//      1 -> A tiles in the SWIZZLE_128B K-major layout (row r of a stage = 128 contiguous bytes, 16-byte chunk c stored at
+//           chunk c ^ (r % 8); what a 2-D TMA load with CU_TENSOR_MAP_SWIZZLE_128B would deposit): eight lanes own the
+//           eight chunks of one row, so a warp load instruction covers 4 whole lines (coalesced) and a quarter-warp's
+//           STS.128 fills the 8 distinct chunk slots of its row (conflict-free).  BK = 32 only (one swizzle atom).
+template <int NORM, int SCALED, int BK, int STAGES, int ASW>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const float *__restrict__ mean,
                        const float *__restrict__ rowscale, const float *__restrict__ Bt, int NT, int upper,
@@ -168,7 +174,10 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
     constexpr int A_BYTES = BM * BK * 4;                             // one of hi / lo: 16 KB (BK = 32) or 8 KB (BK = 16)
     constexpr int SBO = BK * 32;                                     // bytes between 8-row groups of an operand tile
     constexpr int Q = BK / 4;                                        // float4 per row and stage
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    static_assert(!ASW || BK == 32, "the swizzled A layout is one 128-byte atom per row");
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    // 1024-byte alignment: the SWIZZLE_128B pattern is a function of the shared-memory address bits [4, 10)
+    unsigned char *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int halves = NT > NMAX ? 2 : 1;                            // column halves of a row tile (two accumulator passes)
     const int N = NT / halves;                                       // UMMA N
     const int b_bytes = N * BK * 4;                                  // one of hi / lo, one half
@@ -208,7 +217,73 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < 4 && ASW) {
+        // ------------------------------------------------------------------ A producers, swizzled tiles (8 lanes = one row)
+        // lane -> (rsub = lane / 8, chunk q = lane % 8); the thread owns chunk q of rows 32*warp + 4*j + rsub, j = 0..7.
+        const int rsub = lane >> 3, q = lane & 7;
+        const int per_tile = halves * n_chunks;
+        const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t total = my_tiles * steps_per_tile;
+        auto advance = [&](int64_t &t, int &p) {       // next executed (half, chunk) step
+            do {
+                if (++p == per_tile) { p = 0; t += gridDim.x; }
+            } while (first_col(p / n_chunks, p % n_chunks) >= N);
+        };
+        float4 cur[8], nxt[8];
+        auto fetch = [&](int64_t tile, int c, float4 (&v)[8]) {
+            const int64_t row0 = tile * BM + warp * 32 + rsub;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t row = row0 + 4 * j;
+                v[j] = row < n ? __ldg(reinterpret_cast<const float4 *>(x + row * (int64_t)d + c * BK) + q)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        int64_t tile = blockIdx.x;
+        int pos = 0;
+        if (total > 0) fetch(tile, 0, cur);
+        float rs[8];
+        int64_t rs_tile = -1;
+        uint32_t it = 0;
+        for (int64_t i = 0; i < total; ++i, ++it) {
+            const int c = pos % n_chunks;
+            int64_t ntile = tile;
+            int npos = pos;
+            if (i + 1 < total) { advance(ntile, npos); fetch(ntile, npos % n_chunks, nxt); }
+            const int64_t row0 = tile * BM + warp * 32 + rsub;
+            if (SCALED && rs_tile != tile) {           // A*1 of this thread's 8 rows, once per tile
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rs[j] = row0 + 4 * j < n ? __ldg(rowscale + row0 + 4 * j) : 0.f;
+                rs_tile = tile;
+            }
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            const float4 m0 = __ldg(reinterpret_cast<const float4 *>(mean + c * BK) + q);
+            mbar_wait(&empty[s], ph ^ 1);              // stage free (first round passes immediately)
+            unsigned char *hi = sA + s * 2 * A_BYTES, *lo = hi + A_BYTES;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = warp * 32 + 4 * j + rsub;                     // row of the tile
+                const bool in = row0 + 4 * j < n;
+                float4 m = m0;
+                if (SCALED) { m.x = __fmul_rn(rs[j], m.x); m.y = __fmul_rn(rs[j], m.y); m.z = __fmul_rn(rs[j], m.z); m.w = __fmul_rn(rs[j], m.w); }
+                float4 a, hh, l;
+                a.x = in ? __fsub_rn(cur[j].x, m.x) : 0.f; a.y = in ? __fsub_rn(cur[j].y, m.y) : 0.f;
+                a.z = in ? __fsub_rn(cur[j].z, m.z) : 0.f; a.w = in ? __fsub_rn(cur[j].w, m.w) : 0.f;
+                hh.x = tf32_hi(a.x); hh.y = tf32_hi(a.y); hh.z = tf32_hi(a.z); hh.w = tf32_hi(a.w);
+                l.x = a.x - hh.x; l.y = a.y - hh.y; l.z = a.z - hh.z; l.w = a.w - hh.w;
+                const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((q ^ (r & 7)) << 4);
+                *reinterpret_cast<float4 *>(hi + off) = hh;
+                *reinterpret_cast<float4 *>(lo + off) = l;
+            }
+            fence_proxy_async();                       // generic-proxy smem writes -> visible to the tensor core
+            mbar_arrive(&full_a[s]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+            tile = ntile;
+            pos = npos;
+        }
+    } else if (warp < 4) {
         // ------------------------------------------------------------------ A producers (thread = row of the tile)
         // The global loads of step i+1 are issued before step i is converted: a producer that loads, waits and
         // converts one chunk at a time spends most of each step in the load latency (ncu, round 2: the first use of the
@@ -368,7 +443,10 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k) {                 // UMMA K = 8 tf32 = two 16-byte core columns
                             const uint32_t ko = k * 256;
-                            const uint64_t dah = make_desc(a_hi + ko, 128, SBO), dal = make_desc(a_lo + ko, 128, SBO);
+                            // swizzled A: the K step moves 32 bytes inside the 128-byte rows (LBO field unused = 16 B), rows
+                            // groups are 1024 bytes apart; the hardware applies the XOR from the address bits
+                            const uint64_t dah = ASW ? make_desc(a_hi + k * 32, 16, 1024) | (2ull << 61) : make_desc(a_hi + ko, 128, SBO);
+                            const uint64_t dal = ASW ? make_desc(a_lo + k * 32, 16, 1024) | (2ull << 61) : make_desc(a_lo + ko, 128, SBO);
                             const uint64_t dbh = make_desc(b_hi + ko, 128, SBO), dbl = make_desc(b_lo + ko, 128, SBO);
                             mma_tf32(tmem_c, dal, dbh, idesc_c, (c | k) != 0);   // small terms first
                             mma_tf32(tmem_c, dah, dbl, idesc_c, 1);
@@ -424,6 +502,12 @@ std::atomic<int> g_k3_bk{[] {
     return (v == 16 || v == 32) ? v : 32;
 }()};
 
+// A-tile layout of K3 (BK = 32): 0 = row-per-thread producers / no swizzle, 1 = coalesced producers / SWIZZLE_128B.
+std::atomic<int> g_k3_asw{[] {
+    const char *e = getenv("CLEORA_B200_K3_ASW");
+    return e ? (atoi(e) != 0 ? 1 : 0) : 0;
+}()};
+
 bool whiten_apply_tc_supported(int64_t d, int64_t dout) {
     if (d % tc::BK_MAX != 0 || d < tc::BK_MAX || dout < 16) return false;
     if (dout <= tc::NMAX) return dout % 32 == 0;                    // the epilogue moves 32-column blocks
@@ -448,7 +532,7 @@ void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *m
     LAUNCH_CHECK();
     const int NT = (int)dout, N = NT > NMAX ? NT / 2 : NT;
     const size_t smem = (size_t)stages * 2 * (BM * bk * 4) + (size_t)stages * 2 * N * bk * 4 + EPI_BYTES +
-                        (3 * stages + 4) * sizeof(uint64_t) + 16;
+                        (3 * stages + 4) * sizeof(uint64_t) + 16 + 1024;      // + slack for the 1024-byte alignment
     const int64_t n_tiles = (n + BM - 1) / BM;
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
     auto launch = [&](auto kernel) {
@@ -459,8 +543,9 @@ void launch_whiten_apply_tc(const float *x, int64_t n, int64_t d, const float *m
     if (norm != CLEORA_NORM_NONE && !l2) throw CudaFail{"tensor-core apply: unsupported fused normalisation"};
     auto pick = [&](auto norm_c, auto scaled_c) {
         constexpr int NORM = decltype(norm_c)::value, SCALED = decltype(scaled_c)::value;
-        if (bk == 16) launch(whiten_apply_tc_kernel<NORM, SCALED, 16, 4>);
-        else launch(whiten_apply_tc_kernel<NORM, SCALED, 32, 2>);
+        if (bk == 16) launch(whiten_apply_tc_kernel<NORM, SCALED, 16, 4, 0>);
+        else if (g_k3_asw.load()) launch(whiten_apply_tc_kernel<NORM, SCALED, 32, 2, 1>);
+        else launch(whiten_apply_tc_kernel<NORM, SCALED, 32, 2, 0>);
     };
     using std::integral_constant;
     if (rowscale) { if (l2) pick(integral_constant<int, CLEORA_NORM_L2_NUMPY>{}, integral_constant<int, 1>{}); else pick(integral_constant<int, 0>{}, integral_constant<int, 1>{}); }

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""K3 (whiten_apply_tc_kernel) stage-shape A/B: (BK 32, 2 stages) vs (BK 16, 4 stages), on the variants the loop
+"""K3 (whiten_apply_tc_kernel) A/B: (BK 32, 2 stages) vs the same with coalesced producers and SWIZZLE_128B A tiles vs
+(BK 16, 4 stages), on the variants the loop
 launches -- plain apply, fused row norm + row scale (pipelined loop), and the same with an upper-triangular transform
 (Cholesky inner iterations).  Prints time per launch and the error against an f64 reference of the first rows; the two
 shapes must agree bit for bit (same products in the same order per accumulator column)."""
@@ -14,6 +15,10 @@ import torch  # noqa: E402
 from cleora_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
+# (name, K floats per stage, A-tile layout): round-1 shape | coalesced producers + SWIZZLE_128B A tiles | 4 half-size stages
+VARIANTS = [("bk32", 32, 0), ("bk32+asw", 32, 1), ("bk16x4", 16, 0)]
+if len(sys.argv) > 1:
+    VARIANTS = [v for v in VARIANTS if v[0] in sys.argv[1].split(",")]
 
 
 def run_case(n, d, fused, upper, reps=8):
@@ -28,8 +33,9 @@ def run_case(n, d, fused, upper, reps=8):
     xd, md, Td, rd = (torch.from_numpy(a).cuda() for a in (x, mean, np.ascontiguousarray(T), rowscale))
     st = torch.cuda.current_stream().cuda_stream
     outs = {}
-    for bk in (32, 16):
+    for name, bk, asw in VARIANTS:
         _lib.check(L.cleora_set_option(b"k3_bk", bk))
+        _lib.check(L.cleora_set_option(b"k3_asw", asw))
         out = torch.empty(n, d, dtype=torch.float32, device="cuda")
 
         def go():
@@ -54,10 +60,10 @@ def run_case(n, d, fused, upper, reps=8):
             ref /= np.maximum(np.linalg.norm(ref, axis=1, keepdims=True), 1e-10)
         got = out[:m].cpu().numpy()
         err = float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
-        outs[bk] = out
-        print(f"n={n} d={d} fused={int(fused)} upper={int(upper)} bk={bk}: {ms:.3f} ms  err/scale {err:.2e}", flush=True)
-    same = bool(torch.equal(outs[32], outs[16]))
-    print(f"    bk=16 output identical to bk=32: {same}", flush=True)
+        outs[name] = out
+        print(f"n={n} d={d} fused={int(fused)} upper={int(upper)} {name}: {ms:.3f} ms  err/scale {err:.2e}", flush=True)
+    same = all(bool(torch.equal(outs[VARIANTS[0][0]], outs[v[0]])) for v in VARIANTS[1:])
+    print(f"    all variants identical to {VARIANTS[0][0]}: {same}", flush=True)
     return same
 
 
@@ -67,4 +73,5 @@ if __name__ == "__main__":
         for fused, upper in [(False, False), (True, False), (True, True)]:
             ok &= run_case(n, d, fused, upper)
     _lib.check(L.cleora_set_option(b"k3_bk", 32))
+    _lib.check(L.cleora_set_option(b"k3_asw", 0))
     print("ALL IDENTICAL" if ok else "MISMATCH")
