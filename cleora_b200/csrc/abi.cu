@@ -708,6 +708,7 @@ extern "C" int cleora_set_option(const char *key, int64_t value) {
         if (k == "pipeline_whiten") g_opt_pipeline.store(value != 0);
         else if (k == "chol_whiten") g_opt_chol.store(value != 0);
         else if (k == "k3_asw") g_k3_asw.store(value != 0);
+        else if (k == "gram_needed_cols") g_gram_needed_only.store(value != 0);
         else if (k == "k3_bk") {
             if (value != 16 && value != 32) value_error("k3_bk must be 16 or 32");
             g_k3_bk.store((int)value);
@@ -721,6 +722,7 @@ extern "C" int64_t cleora_get_option(const char *key) {
     if (k == "chol_whiten") return g_opt_chol.load();
     if (k == "k3_bk") return g_k3_bk.load();
     if (k == "k3_asw") return g_k3_asw.load();
+    if (k == "gram_needed_cols") return g_gram_needed_only.load();
     return -1;
 }
 extern "C" int cleora_host_alloc(size_t nbytes, void **out) {

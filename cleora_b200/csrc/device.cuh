@@ -146,6 +146,7 @@ std::unique_ptr<Graph> build_from_pairs_device(const uint32_t *u, const uint32_t
                                                cudaStream_t st, std::vector<int64_t> *bounds_out);
 void synth_pairs_device(int kind, int64_t n_nodes, int64_t n_pairs, uint64_t seed, double alpha, uint32_t *u, uint32_t *v,
                         cudaStream_t st);
+extern std::atomic<int> g_gram_needed_only;   // int8 Gram, d = 256: convert only the columns a tile reads (gram_tc.cu)
 // Cholesky whitening (chol_whiten.cu): T = L^-T of cov = L L^T as f32; status[0] raised when cov is not safely SPD.
 bool chol_whiten_supported(int64_t d);
 void launch_chol_whiten(const double *cov, int64_t d, float *T, int *status, cudaStream_t st);

@@ -33,6 +33,7 @@
 #include "../../include/cleora_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <string>
 
@@ -201,11 +202,12 @@ __global__ void quant_params_kernel(const float *__restrict__ absmax_partial, in
 //   true : K-major  -- core matrix = 8 columns (MN) x 16 rows (K); a converter thread owns one column of 16 rows.
 // Measured (n = 1M, d = 256 / n = 300k, d = 128): MN-major 1.88 / 0.30 ms, K-major 2.29 / 0.24 ms -- the launcher
 // picks MN-major for d = 256 and K-major for d = 128 (where the MN-major mapping leaves half the converters idle).
-template <bool KMAJOR>
+template <bool KMAJOR, bool NEEDED>
 __global__ void __launch_bounds__(g8::THREADS, 1)
 gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantParams *__restrict__ qp,
                const int32_t *__restrict__ m_int, long long *__restrict__ G /* [7][d][d] */,
                long long *__restrict__ colsum /* [d] */, int64_t rows_per_slice) {
+    constexpr bool needed_only = NEEDED;
     using namespace g8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int plane_bytes = ROWS * d;                                 // one byte plane of one stage
@@ -239,7 +241,11 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
         if (t < cnt) { js = first + t; break; }
         t -= cnt;
     }
-    const bool owns_colsum = blockIdx.x == 0;
+    // needed_only (MN-major planes, d = 256): a tile reads only the columns of its row block and of its stripe -- 128 of
+    // the 256 columns when the stripe lies inside the block, 192 otherwise -- so only those are converted (42 % fewer
+    // conversions and plane bytes over the six tiles of a row slice); the exact column sums are then taken by the first
+    // tile of each block row for that block's columns.
+    const bool owns_colsum = needed_only ? (js == mb * (128 / STRIPE)) : blockIdx.x == 0;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice, r1 = min(n, r0 + rows_per_slice);
     const int n_stages = (int)((r1 - r0 + ROWS - 1) / ROWS);
     const int n_cg = d / 16;                                          // 16-byte column groups per row
@@ -318,6 +324,80 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             mbar_arrive(&raw_empty[rs]);
         }
         if (owns_colsum && csum != 0) atomicAdd(reinterpret_cast<unsigned long long *>(colsum + j), (unsigned long long)csum);
+      } else if constexpr (NEEDED) {
+        // ------------------------------------------------------------ converters, MN-major planes, needed columns only
+        // item = (16-column group g, stage row rr); items 0..255 = the 8 groups of row block mb, items 256..383 = the 4
+        // groups of stripe js when it lies outside the block.  Thread t owns item t and, in warps 0-3 of such a tile,
+        // item 256 + t.  A quarter-warp = 8 consecutive rows of one group: conflict-free LDS.128 / STS.128 as below.
+        const int rr = threadIdx.x & 31, gi = threadIdx.x >> 5;               // gi = 0..7
+        const int blk0 = mb * 8, str0 = js * (STRIPE / 16);
+        const bool stripe_outside = str0 < blk0 || str0 >= blk0 + 8;
+        const int cg_a = blk0 + gi;
+        const bool has_b = stripe_outside && gi < STRIPE / 16;
+        const int cg_b = has_b ? str0 + gi : cg_a;
+        const float scale = qp->scale;
+        int4 mia[4];                                     // (the second item's centres are re-read from L1 each stage: registers)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mia[q] = __ldg(reinterpret_cast<const int4 *>(m_int + cg_a * 16) + q);
+        long long csum[16];                              // exact column sums of q over this thread's rows (block columns)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) csum[c] = 0;
+        for (int st = 0; st < n_stages; ++st) {
+            const int rs = st % RAW_STAGES, s = st % PS;
+            mbar_wait(&raw_full[rs], (st / RAW_STAGES) & 1);
+            mbar_wait(&empty[s], ((st / PS) & 1) ^ 1);
+            const unsigned char *raw = sR + rs * raw_bytes;
+            unsigned char *base = sP + s * stage_bytes;
+            const int64_t row = r0 + (int64_t)st * ROWS + rr;
+            const unsigned char *xrow = raw + rr * raw_stride;
+#pragma unroll 1
+            for (int item = 0; item < 2; ++item) {
+                if (item == 1 && !has_b) break;
+                const int cg = item ? cg_b : cg_a;
+                int qv[16];
+                if (row < r1) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 v = *reinterpret_cast<const float4 *>(xrow + (((cg * 4 + q) ^ (rr & 7)) << 4));
+                        const int4 m = item ? __ldg(reinterpret_cast<const int4 *>(m_int + cg_b * 16) + q) : mia[q];
+                        qv[4 * q + 0] = __float2int_rn(v.x * scale) - m.x;
+                        qv[4 * q + 1] = __float2int_rn(v.y * scale) - m.y;
+                        qv[4 * q + 2] = __float2int_rn(v.z * scale) - m.z;
+                        qv[4 * q + 3] = __float2int_rn(v.w * scale) - m.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) qv[c] = 0;
+                }
+                const uint32_t off = (uint32_t)((rr & 7) * 16 + (rr >> 3) * 128 + cg * (ROWS / 8) * 128);
+                uint4 pl[4];
+#pragma unroll
+                for (int wq = 0; wq < 4; ++wq) {
+                    const uint32_t a = (uint32_t)qv[4 * wq], b2 = (uint32_t)qv[4 * wq + 1];
+                    const uint32_t c2 = (uint32_t)qv[4 * wq + 2], d2 = (uint32_t)qv[4 * wq + 3];
+                    const uint32_t t0 = __byte_perm(a, b2, 0x5140), t1 = __byte_perm(a, b2, 0x7362);
+                    const uint32_t t2 = __byte_perm(c2, d2, 0x5140), t3 = __byte_perm(c2, d2, 0x7362);
+                    (&pl[0].x)[wq] = __byte_perm(t0, t2, 0x5410);
+                    (&pl[1].x)[wq] = __byte_perm(t0, t2, 0x7632);
+                    (&pl[2].x)[wq] = __byte_perm(t1, t3, 0x5410);
+                    (&pl[3].x)[wq] = __byte_perm(t1, t3, 0x7632);
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p) *reinterpret_cast<uint4 *>(base + p * plane_bytes + off) = pl[p];
+                if (owns_colsum && item == 0) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) csum[c] += qv[c];
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&full[s]);
+            mbar_arrive(&raw_empty[rs]);
+        }
+        if (owns_colsum) {                              // integer atomics: exact and order-independent
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (csum[c] != 0) atomicAdd(reinterpret_cast<unsigned long long *>(colsum + cg_a * 16 + c), (unsigned long long)csum[c]);
+        }
       } else {
         // ------------------------------------------------------------ converters: raw f32 (smem) -> 4 byte planes
         // thread -> (row lane rl = tid % 8, column group cg = (tid / 8) % 16, half h = tid / 128); it converts rows
@@ -508,6 +588,11 @@ __global__ void gram_i8_combine_kernel(const long long *__restrict__ G, const lo
     cov[idx] = ldexp(acc, -2 * qp->e);
 }
 
+std::atomic<int> g_gram_needed_only{[] {
+    const char *e = getenv("CLEORA_B200_GRAM_COLS");
+    return (e && std::string(e) == "all") ? 0 : (e && std::string(e) == "needed") ? 1 : 0;
+}()};
+
 bool gram_i8_supported(int64_t n, int64_t d) { return (d == 128 || d == 256) && n >= 4096; }
 
 void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st,
@@ -549,7 +634,9 @@ void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double 
         return v == "mn" ? 0 : v == "k" ? 1 : -1;
     }();
     const bool kmajor = forced >= 0 ? forced == 1 : d < 256;
-    auto kernel = kmajor ? gram_i8_kernel<true> : gram_i8_kernel<false>;
+    // convert only the columns a tile reads (MN-major path, two row blocks): option "gram_needed_cols"
+    const bool needed_only = !kmajor && d == 256 && g_gram_needed_only.load() != 0;
+    auto kernel = kmajor ? gram_i8_kernel<true, false> : (needed_only ? gram_i8_kernel<false, true> : gram_i8_kernel<false, false>);
     const int threads = THREADS;
     // per device, not per process: set on every launch (a host-side table write)
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -313,7 +313,22 @@ def test_mean_and_covariance_f64(n, d):
     np.testing.assert_array_equal(cov, cov.T)
 
 
-def test_integer_gram_on_tensor_cores_is_exact():
+@pytest.fixture(params=["defaults", "k3_asw=1", "k3_asw=0", "k3_bk=16", "gram_needed_cols=1", "gram_needed_cols=0"])
+def kernel_variant(request):
+    """Runs a test under every selectable kernel variant (cleora_set_option): K3's A-tile layout / stage shape and K2b's
+    converted-column set.  Whatever the shipped default is, the alternatives stay green."""
+    L = _lib.lib()
+    keys = (b"k3_asw", b"k3_bk", b"gram_needed_cols")
+    saved = {k: L.cleora_get_option(k) for k in keys}
+    if request.param != "defaults":
+        k, v = request.param.split("=")
+        _lib.check(L.cleora_set_option(k.encode(), int(v)))
+    yield request.param
+    for k, v in saved.items():
+        _lib.check(L.cleora_set_option(k, v))
+
+
+def test_integer_gram_on_tensor_cores_is_exact(kernel_variant):
     """K2b's tcgen05 kind::i8 path (d in {128, 256}, n >= 4096): for inputs that are exactly representable in its
     fixed-point format the centred Gram matrix must equal the exact rational result -- checked with Python
     integers -- and on generic f32 data it must agree with the f64 oracle to the quantisation bound."""
@@ -345,7 +360,7 @@ def test_integer_gram_on_tensor_cores_is_exact():
 
 
 @pytest.mark.parametrize("n,d,dout", [(3000, 48, 48), (5000, 256, 256), (777, 100, 100), (1000, 64, 10), (4097, 512, 512)])
-def test_apply_transform_given_identical_T(n, d, dout):
+def test_apply_transform_given_identical_T(n, d, dout, kernel_variant):
     import torch
     rs = np.random.default_rng(d)
     x = oracle.normalize(rs.standard_normal((n, d)).astype(np.float32))
@@ -364,7 +379,7 @@ def test_apply_transform_given_identical_T(n, d, dout):
 
 
 @pytest.mark.parametrize("n,d", [(5000, 256), (3000, 128), (4097, 512), (1000, 64)])
-def test_apply_with_upper_triangular_transform(n, d):
+def test_apply_with_upper_triangular_transform(n, d, kernel_variant):
     """K3's zero-block skipping for an upper-triangular T (the Cholesky whitening transform) against the dense path of the
     same kernel and against numpy."""
     import torch
@@ -595,6 +610,12 @@ def test_benchmarked_configuration_40_iterations_er200k(er200k_pair, d):
     got_ref_order = _with_options(lambda: cb.embed(g, d, 40), pipeline_whiten=0)
     assert procrustes_err(got_ref_order, ref) <= 1e-4
     assert gram_err(got_ref_order, ref) <= 1e-5
+    # the selectable kernel variants (both settings of each, whatever the default): same bars, and -- the variants being
+    # re-arrangements of identical arithmetic -- the same bits
+    alt = _with_options(lambda: cb.embed(g, d, 40), k3_asw=1, gram_needed_cols=1)
+    base = _with_options(lambda: cb.embed(g, d, 40), k3_asw=0, gram_needed_cols=0)
+    assert procrustes_err(alt, ref) <= 1e-4 and gram_err(alt, ref) <= 1e-5
+    np.testing.assert_array_equal(alt, base)
 
 
 def test_cholesky_fallback_on_rank_deficient_covariance(golden_dir):

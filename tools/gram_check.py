@@ -26,13 +26,23 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
 
         def run():
             _lib.check(L.cleora_dev_centered_gram(x.data_ptr(), n, d, mean.data_ptr(), cov.data_ptr(), st))
-        run(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            run()
-        e1.record(); torch.cuda.synchronize()
-        c = cov.cpu().numpy()
+        results = {}
+        for needed in ((0, 1) if mode == "i8" else (0,)):          # int8 path: all columns converted vs only the needed ones
+            _lib.check(L.cleora_set_option(b"gram_needed_cols", needed))
+            cov.zero_()
+            run(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                run()
+            e1.record(); torch.cuda.synchronize()
+            results[needed] = cov.cpu().numpy().copy()
+            if mode == "i8":
+                print(f"[i8 needed_cols={needed}] n={n} d={d}: {e0.elapsed_time(e1) / 5:.3f} ms", flush=True)
+        if mode == "i8":
+            print(f"[i8] n={n} d={d}: needed-columns result identical to all-columns: "
+                  f"{bool(np.array_equal(results[0], results[1]))}", flush=True)
+        c = results[max(results)]
         ref = torch.cov(x[:200000].double().T).cpu().numpy() if n >= 200000 else None
         np.save(f"/tmp/gram_{mode}_{n}_{d}.npy", c)
         sym = float(np.max(np.abs(c - c.T)) / np.max(np.abs(c)))
