@@ -590,7 +590,7 @@ __global__ void gram_i8_combine_kernel(const long long *__restrict__ G, const lo
 
 std::atomic<int> g_gram_needed_only{[] {
     const char *e = getenv("CLEORA_B200_GRAM_COLS");
-    return (e && std::string(e) == "all") ? 0 : (e && std::string(e) == "needed") ? 1 : 0;
+    return (e && std::string(e) == "all") ? 0 : 1;
 }()};
 
 bool gram_i8_supported(int64_t n, int64_t d) { return (d == 128 || d == 256) && n >= 4096; }

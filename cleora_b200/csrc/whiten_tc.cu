@@ -361,14 +361,20 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
             float scale = 1.f;
             uint32_t v[32];
             if (NORM == CLEORA_NORM_L2_NUMPY) {
-                float ss = 0.f;
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};         // four interleaved partial sums: a 4x shorter dependency chain
                 for (int h = 0; h < halves; ++h)
                     for (int c0 = 0; c0 < N; c0 += 32) {
                         tmem_ld32(taddr[h] + c0, v);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) { const float f = __uint_as_float(v[j]); ss = fmaf(f, f, ss); }
+                        for (int j = 0; j < 32; ++j) { const float f = __uint_as_float(v[j]); s4[j & 3] = fmaf(f, f, s4[j & 3]); }
                     }
-                scale = fmaxf(sqrtf(ss), 1e-10f);
+                const float ss = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                // One IEEE division per row, then a multiplication per element.  (Round 2, profiles/r2n: 256 inline
+                // __fdiv_rn per row -- MUFU.RCP + Newton steps + a range check with a slow-path call each, ~28 SASS
+                // instructions, serialised by the checks -- made this epilogue the bound of the whole kernel: 1.01 ms
+                // for every main-loop variant.  The product differs from x / norm by at most 1 ulp, far below the
+                // 3xTF32 error of the GEMM that produced x, and K3's rows have no bit-exact counterpart elsewhere.)
+                scale = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), 1e-10f));
             }
             for (int h = 0; h < halves; ++h)
                 for (int c0 = 0; c0 < N; c0 += 32) {
@@ -380,8 +386,8 @@ whiten_apply_tc_kernel(const float *__restrict__ x, int64_t n, int d, const floa
                         o.x = __uint_as_float(v[4 * j + 0]); o.y = __uint_as_float(v[4 * j + 1]);
                         o.z = __uint_as_float(v[4 * j + 2]); o.w = __uint_as_float(v[4 * j + 3]);
                         if (NORM == CLEORA_NORM_L2_NUMPY) {
-                            o.x = __fdiv_rn(o.x, scale); o.y = __fdiv_rn(o.y, scale);
-                            o.z = __fdiv_rn(o.z, scale); o.w = __fdiv_rn(o.w, scale);
+                            o.x = __fmul_rn(o.x, scale); o.y = __fmul_rn(o.y, scale);
+                            o.z = __fmul_rn(o.z, scale); o.w = __fmul_rn(o.w, scale);
                         }
                         *reinterpret_cast<float4 *>(tile_s + lane * EPI_LD + 4 * j) = o;
                     }
@@ -505,7 +511,7 @@ std::atomic<int> g_k3_bk{[] {
 // A-tile layout of K3 (BK = 32): 0 = row-per-thread producers / no swizzle, 1 = coalesced producers / SWIZZLE_128B.
 std::atomic<int> g_k3_asw{[] {
     const char *e = getenv("CLEORA_B200_K3_ASW");
-    return e ? (atoi(e) != 0 ? 1 : 0) : 0;
+    return e ? (atoi(e) != 0 ? 1 : 0) : 1;
 }()};
 
 bool whiten_apply_tc_supported(int64_t d, int64_t dout) {
