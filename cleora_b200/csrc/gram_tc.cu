@@ -51,6 +51,7 @@ constexpr int THREADS = CONV_THREADS + 128 + 32 + LOAD_THREADS;   // + 4 drain w
 constexpr int PS = 2;              // plane stages; compile-time, like RAW_STAGES: a runtime modulo in the per-stage
                                    // bookkeeping cost every role ~10 % (measured 2.10 -> 1.88 ms)
 constexpr int RAW_STAGES = 4;
+constexpr int NGC = 12;            // compact staging (NEEDED): 16-column groups per tile = 8 of the row block + 4 of the stripe
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -210,14 +211,18 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
     constexpr bool needed_only = NEEDED;
     using namespace g8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int plane_bytes = ROWS * d;                                 // one byte plane of one stage
+    // NEEDED: only the columns this tile reads are loaded, converted and staged, in a COMPACT layout -- group slots 0..7 =
+    // the 128 columns of row block mb, slots 8..11 = the 64 columns of stripe js when it lies outside the block (inside,
+    // the B operand is a view of slots 0..7).  Shared memory then no longer grows with d (24 KB per plane stage and per
+    // raw stage for every d), which is what admits d = 384 and 512.
+    const int plane_bytes = NEEDED ? ROWS * NGC * 16 : ROWS * d;      // one byte plane of one stage
     const int stage_bytes = 4 * plane_bytes;
     // Raw rows are staged densely (row stride d*4, every cp.async piece 16-byte aligned inside its 128-byte line) with
     // an XOR swizzle: piece p of stage row r lives at piece p ^ (r & 7).  Eight converter lanes that read the same
     // piece index of eight consecutive rows then hit eight different 16-byte slots (conflict-free LDS.128), and a
     // loader quarter-warp still fills exactly one 128-byte line.  (Round 1 skewed the rows by 16 bytes instead, which
     // kept the LDS conflict-free but made most LDGSTS quarter-warps straddle two lines: 102 M wavefronts for 48 M ideal.)
-    const int raw_stride = d * 4;
+    const int raw_stride = NEEDED ? NGC * 64 : d * 4;
     const int raw_bytes = ROWS * raw_stride;
     unsigned char *sP = smem_raw;                                     // [STAGES] byte planes (MMA operands)
     unsigned char *sR = sP + PS * stage_bytes;                        // [RAW_STAGES] raw f32 rows (cp.async ring)
@@ -241,10 +246,10 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
         if (t < cnt) { js = first + t; break; }
         t -= cnt;
     }
-    // needed_only (MN-major planes, d = 256): a tile reads only the columns of its row block and of its stripe -- 128 of
-    // the 256 columns when the stripe lies inside the block, 192 otherwise -- so only those are converted (42 % fewer
-    // conversions and plane bytes over the six tiles of a row slice); the exact column sums are then taken by the first
-    // tile of each block row for that block's columns.
+    // needed_only (MN-major planes): a tile reads only the columns of its row block and of its stripe -- 128 columns when
+    // the stripe lies inside the block, 192 otherwise -- so only those are loaded and converted (at d = 256: 42 % fewer
+    // conversions, plane bytes and cp.async pieces over the six tiles of a row slice); the exact column sums are then
+    // taken by the first tile of each block row for that block's columns.
     const bool owns_colsum = needed_only ? (js == mb * (128 / STRIPE)) : blockIdx.x == 0;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice, r1 = min(n, r0 + rows_per_slice);
     const int n_stages = (int)((r1 - r0 + ROWS - 1) / ROWS);
@@ -326,15 +331,16 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
         if (owns_colsum && csum != 0) atomicAdd(reinterpret_cast<unsigned long long *>(colsum + j), (unsigned long long)csum);
       } else if constexpr (NEEDED) {
         // ------------------------------------------------------------ converters, MN-major planes, needed columns only
-        // item = (16-column group g, stage row rr); items 0..255 = the 8 groups of row block mb, items 256..383 = the 4
-        // groups of stripe js when it lies outside the block.  Thread t owns item t and, in warps 0-3 of such a tile,
-        // item 256 + t.  A quarter-warp = 8 consecutive rows of one group: conflict-free LDS.128 / STS.128 as below.
+        // item = (group slot, stage row rr); items 0..255 = the 8 groups of row block mb (slots 0..7), items 256..383 = the
+        // 4 groups of stripe js when it lies outside the block (slots 8..11).  Thread t owns item t and, in warps 0-3 of
+        // such a tile, item 256 + t.  A quarter-warp = 8 consecutive rows of one group: conflict-free LDS.128 / STS.128.
+        // cg_* = absolute 16-column group (centres, column sums), slot_* = its place in the compact staging.
         const int rr = threadIdx.x & 31, gi = threadIdx.x >> 5;               // gi = 0..7
         const int blk0 = mb * 8, str0 = js * (STRIPE / 16);
         const bool stripe_outside = str0 < blk0 || str0 >= blk0 + 8;
-        const int cg_a = blk0 + gi;
+        const int cg_a = blk0 + gi, slot_a = gi;
         const bool has_b = stripe_outside && gi < STRIPE / 16;
-        const int cg_b = has_b ? str0 + gi : cg_a;
+        const int cg_b = has_b ? str0 + gi : cg_a, slot_b = has_b ? 8 + gi : gi;
         const float scale = qp->scale;
         int4 mia[4];                                     // (the second item's centres are re-read from L1 each stage: registers)
 #pragma unroll
@@ -353,12 +359,12 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
 #pragma unroll 1
             for (int item = 0; item < 2; ++item) {
                 if (item == 1 && !has_b) break;
-                const int cg = item ? cg_b : cg_a;
+                const int slot = item ? slot_b : slot_a;
                 int qv[16];
                 if (row < r1) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float4 v = *reinterpret_cast<const float4 *>(xrow + (((cg * 4 + q) ^ (rr & 7)) << 4));
+                        const float4 v = *reinterpret_cast<const float4 *>(xrow + (((slot * 4 + q) ^ (rr & 7)) << 4));
                         const int4 m = item ? __ldg(reinterpret_cast<const int4 *>(m_int + cg_b * 16) + q) : mia[q];
                         qv[4 * q + 0] = __float2int_rn(v.x * scale) - m.x;
                         qv[4 * q + 1] = __float2int_rn(v.y * scale) - m.y;
@@ -369,7 +375,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
 #pragma unroll
                     for (int c = 0; c < 16; ++c) qv[c] = 0;
                 }
-                const uint32_t off = (uint32_t)((rr & 7) * 16 + (rr >> 3) * 128 + cg * (ROWS / 8) * 128);
+                const uint32_t off = (uint32_t)((rr & 7) * 16 + (rr >> 3) * 128 + slot * (ROWS / 8) * 128);
                 uint4 pl[4];
 #pragma unroll
                 for (int wq = 0; wq < 4; ++wq) {
@@ -501,8 +507,13 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
         // MN-major: LBO = step between 8-row K groups (128 B), SBO = step between 16-column MN groups (512 B);
         // K-major: LBO = step between 16-row K chunks (128 B), SBO = step between 8-column MN groups (256 B).
         const uint32_t lbo = 128, sbo = KMAJOR ? (ROWS / 16) * 128 : (ROWS / 8) * 128;
-        const uint32_t a_off = KMAJOR ? (uint32_t)(mb * 16) * sbo : (uint32_t)(mb * 8) * sbo;        // first MN group of block i
-        const uint32_t b_off = KMAJOR ? (uint32_t)(js * (STRIPE / 8)) * sbo : (uint32_t)(js * (STRIPE / 16)) * sbo;
+        uint32_t a_off = KMAJOR ? (uint32_t)(mb * 16) * sbo : (uint32_t)(mb * 8) * sbo;              // first MN group of block i
+        uint32_t b_off = KMAJOR ? (uint32_t)(js * (STRIPE / 8)) * sbo : (uint32_t)(js * (STRIPE / 16)) * sbo;
+        if (NEEDED) {                                                 // compact staging: block at slot 0, stripe inside it or at slot 8
+            const int blk0 = mb * 8, str0 = js * (STRIPE / 16);
+            a_off = 0;
+            b_off = (uint32_t)((str0 >= blk0 && str0 < blk0 + 8) ? str0 - blk0 : 8) * sbo;
+        }
         for (int st = 0; st < n_stages; ++st) {
             const int s = st % PS;
             const bool first = (st % DRAIN_STAGES) == 0;              // first stage after a drain: overwrite
@@ -540,6 +551,34 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
         // thread -> fixed 16-byte column piece pc and a fixed row phase; it walks down the stage's rows with constant
         // strides (no per-piece division: the first version spent ~80 instructions per piece on index arithmetic)
         const int lt = threadIdx.x - (CONV_WARPS + 5) * 32;            // 0..127
+        if constexpr (NEEDED) {
+            // compact rows: 32 (stripe inside the block) or 48 pieces of 16 bytes = the block's 512 contiguous bytes and,
+            // behind them, the stripe's 256.  Piece i of the stage (row-major, i = rr * ppr + pc) goes to thread i % 128;
+            // (rr, pc) advance incrementally from item to item (no division in the loop).
+            const int blk0 = mb * 8, str0 = js * (STRIPE / 16);
+            const bool outside = str0 < blk0 || str0 >= blk0 + 8;
+            const int ppr = outside ? NGC * 4 : 32;
+            const int n_items = ROWS * ppr / LOAD_THREADS;              // 8 or 12 per thread and stage
+            const int step_rr = LOAD_THREADS / ppr, step_pc = LOAD_THREADS % ppr;
+            for (int st = 0; st < n_stages; ++st) {
+                const int rs = st % RAW_STAGES;
+                mbar_wait(&raw_empty[rs], ((st / RAW_STAGES) & 1) ^ 1);
+                const int64_t row0 = r0 + (int64_t)st * ROWS;
+                const int64_t rows_left = r1 - row0;                    // >= 1
+                unsigned char *stage = sR + rs * raw_bytes;
+                int rr = lt / ppr, pc = lt % ppr;
+                for (int it = 0; it < n_items; ++it) {
+                    const int slot = pc >> 2;
+                    const int col = (slot < 8 ? mb * 128 + slot * 16 : js * STRIPE + (slot - 8) * 16) + (pc & 3) * 4;
+                    const bool in = rr < rows_left;
+                    cp_async_cg16(stage + rr * raw_stride + ((pc ^ (rr & 7)) << 4), in ? x + (row0 + rr) * (int64_t)d + col : x, in ? 16 : 0);
+                    rr += step_rr; pc += step_pc;
+                    if (pc >= ppr) { pc -= ppr; ++rr; }
+                }
+                cp_async_arrive_noinc(&raw_full[rs]);
+            }
+            cp_async_wait_all();
+        } else {
         const int ppr = d / 4;                                          // 16-byte pieces per row: 32 (d=128) or 64 (d=256)
         const int pc = lt % ppr, rr0 = lt / ppr, rstep = LOAD_THREADS / ppr;   // rows rr0, rr0+rstep, ...
         for (int st = 0; st < n_stages; ++st) {
@@ -559,6 +598,7 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             cp_async_arrive_noinc(&raw_full[rs]);
         }
         cp_async_wait_all();
+        }
     }
 
     tc_fence_before();
@@ -593,7 +633,12 @@ std::atomic<int> g_gram_needed_only{[] {
     return (e && std::string(e) == "all") ? 0 : 1;
 }()};
 
-bool gram_i8_supported(int64_t n, int64_t d) { return (d == 128 || d == 256) && n >= 4096; }
+// d = 128, 256: both stagings; d = 384, 512: only with the compact staging of the needed columns (option gram_needed_cols)
+bool gram_i8_supported(int64_t n, int64_t d) {
+    if (n < 4096) return false;
+    if (d == 128 || d == 256) return true;
+    return (d == 384 || d == 512) && g_gram_needed_only.load() != 0;
+}
 
 void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double *mean, double *cov, cudaStream_t st,
                              const AbsmaxPartials *known_absmax) {
@@ -626,7 +671,6 @@ void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double 
     int64_t slices = std::max<int64_t>(1, std::min<int64_t>(148 / stripes, (n + 4 * ROWS - 1) / (4 * ROWS)));   // one wave
     const int64_t rows_per_slice = ((n + slices - 1) / slices + ROWS - 1) / ROWS * ROWS;
     slices = (n + rows_per_slice - 1) / rows_per_slice;
-    const size_t smem = (size_t)PS * 4 * ROWS * d + (size_t)RAW_STAGES * ROWS * (d * 4) + (4 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
     // plane layout: CLEORA_B200_GRAM_LAYOUT=mn|k overrides the per-shape default (see the kernel's comment)
     static const int forced = [] {
         const char *e = getenv("CLEORA_B200_GRAM_LAYOUT");
@@ -635,7 +679,11 @@ void launch_centered_gram_i8(const float *x, int64_t n, int64_t d, const double 
     }();
     const bool kmajor = forced >= 0 ? forced == 1 : d < 256;
     // convert only the columns a tile reads (MN-major path, two row blocks): option "gram_needed_cols"
-    const bool needed_only = !kmajor && d == 256 && g_gram_needed_only.load() != 0;
+    const bool needed_only = !kmajor && d >= 256 && g_gram_needed_only.load() != 0;
+    if (d > 256 && !needed_only) throw CudaFail{"integer Gram: d > 256 needs the compact staging (gram_needed_cols = 1, MN-major planes)"};
+    const size_t smem = (needed_only ? (size_t)(PS + RAW_STAGES) * 4 * ROWS * NGC * 16
+                                     : (size_t)PS * 4 * ROWS * d + (size_t)RAW_STAGES * ROWS * (d * 4)) +
+                        (4 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
     auto kernel = kmajor ? gram_i8_kernel<true, false> : (needed_only ? gram_i8_kernel<false, true> : gram_i8_kernel<false, false>);
     const int threads = THREADS;
     // per device, not per process: set on every launch (a host-side table write)

@@ -193,6 +193,12 @@ void cleora_set_eigh_thread(int mode, cleora_eigh_fn fn, void *user);
  *   right-multiplication, so the final iterate (always PCA-whitened) is the reference's.  Falls back to the
  *   eigensolver for the whole call when a covariance is not safely positive definite (lambda_min near the reference's
  *   1e-10 clamp).  0 = eigensolver in every iteration.
+ * "gram_needed_cols" (default 1): the integer tensor-core Gram kernel (d = 256, 384, 512) loads, converts and stages
+ *   only the columns a tile reads -- its 128-column row block and its 64-column stripe -- in a compact shared-memory
+ *   layout whose size does not depend on d; 0 = stage all d columns (d <= 256 only; d = 384 / 512 then use the FP64
+ *   DMMA kernel).  Results are bit-identical (exact integer arithmetic either way).
+ * "k3_asw" (default 1): A tiles of the tensor-core apply kernel in the SWIZZLE_128B K-major layout, written by coalesced
+ *   producers (8 lanes per 128-byte row); 0 = one thread per row, no-swizzle layout.  Identical results.
  * "k3_bk" (32 or 16): stage shape of the tensor-core apply kernel -- 32 floats of K per stage, 2 stages, or 16 floats and
  *   4 stages (same shared memory, refills overlap three stage times instead of one); results are identical. */
 int cleora_set_option(const char *key, int64_t value);

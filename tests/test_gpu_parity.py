@@ -305,7 +305,8 @@ def _dev_stats(x):
 def test_mean_and_covariance_f64(n, d):
     rs = np.random.default_rng(n + d)
     x = oracle.normalize((rs.standard_normal((n, d)) * rs.uniform(0.2, 3.0, d) + rs.uniform(-1, 1, d)).astype(np.float32))
-    mean, gram = _dev_stats(x)
+    # (d = 512 with n >= 4096 would take the integer tensor-core path since round 2; this test is about the IEEE f64 kernel)
+    mean, gram = _with_options(lambda: _dev_stats(x), gram_needed_cols=0) if d > 256 else _dev_stats(x)
     ref_mean, ref_cov = oracle.whiten_stats(x)
     np.testing.assert_allclose(mean, ref_mean, rtol=1e-12, atol=1e-15)
     cov = gram / (n - 1)
@@ -329,11 +330,14 @@ def kernel_variant(request):
 
 
 def test_integer_gram_on_tensor_cores_is_exact(kernel_variant):
-    """K2b's tcgen05 kind::i8 path (d in {128, 256}, n >= 4096): for inputs that are exactly representable in its
+    """K2b's tcgen05 kind::i8 path (d in {128, 256}, and 384 / 512 with the compact staging; n >= 4096): for inputs that are exactly representable in its
     fixed-point format the centred Gram matrix must equal the exact rational result -- checked with Python
     integers -- and on generic f32 data it must agree with the f64 oracle to the quantisation bound."""
     rs = np.random.default_rng(5)
-    for n, d in ((5000, 128), (20000, 256), (4096 + 77, 256)):
+    shapes = [(5000, 128), (20000, 256), (4096 + 77, 256)]
+    if _lib.lib().cleora_get_option(b"gram_needed_cols") == 1:
+        shapes += [(9000, 512), (5000, 384)]                   # four / three row blocks: only with the compact staging
+    for n, d in shapes:
         # multiples of 2^-20 in (-1, 1): exactly representable in f32 and in the kernel's 2^-e grid (e >= 29)
         k = rs.integers(-(2 ** 20) + 1, 2 ** 20, size=(n, d))
         k[:, 3] //= 4096                                        # a column of small values (low planes only)

@@ -7,6 +7,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+SHAPES = [(1_000_000, 256), (300_000, 128), (1_000_000, 512), (500_000, 384)]
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import torch
@@ -14,7 +15,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     L = _lib.lib()
     mode = os.environ.get("CLEORA_B200_GRAM", "i8")
     out = {}
-    for n, d in [(1_000_000, 256), (300_000, 128)]:
+    for n, d in SHAPES:
         g = torch.Generator(device="cuda").manual_seed(n + d)
         x = torch.randn(n, d, device="cuda", generator=g) * torch.linspace(0.3, 2.0, d, device="cuda") + 0.1
         x = torch.nn.functional.normalize(x, dim=1).contiguous()
@@ -27,7 +28,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         def run():
             _lib.check(L.cleora_dev_centered_gram(x.data_ptr(), n, d, mean.data_ptr(), cov.data_ptr(), st))
         results = {}
-        for needed in ((0, 1) if mode == "i8" else (0,)):          # int8 path: all columns converted vs only the needed ones
+        for needed in (((0, 1) if d <= 256 else (1,)) if mode == "i8" else (0,)):   # int8: all columns staged vs the needed ones (d > 256: compact only)
             _lib.check(L.cleora_set_option(b"gram_needed_cols", needed))
             cov.zero_()
             run(); torch.cuda.synchronize()
@@ -39,7 +40,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             results[needed] = cov.cpu().numpy().copy()
             if mode == "i8":
                 print(f"[i8 needed_cols={needed}] n={n} d={d}: {e0.elapsed_time(e1) / 5:.3f} ms", flush=True)
-        if mode == "i8":
+        if mode == "i8" and d <= 256:
             print(f"[i8] n={n} d={d}: needed-columns result identical to all-columns: "
                   f"{bool(np.array_equal(results[0], results[1]))}", flush=True)
         c = results[max(results)]
@@ -55,7 +56,7 @@ else:
             print(r.stdout[-2500:], r.stderr[-2500:], flush=True)
         except subprocess.TimeoutExpired as e:
             print(f"[{mode}] TIMEOUT", (e.stdout or b"")[-2000:], flush=True)
-    for n, d in [(1_000_000, 256), (300_000, 128)]:
+    for n, d in SHAPES:
         try:
             a, b = np.load(f"/tmp/gram_i8_{n}_{d}.npy"), np.load(f"/tmp/gram_v3_{n}_{d}.npy")
             print(f"i8 vs DMMA n={n} d={d}: max|diff|/max|cov| = {np.max(np.abs(a - b)) / np.max(np.abs(b)):.3e}", flush=True)
