@@ -560,20 +560,35 @@ gram_i8_kernel(const float *__restrict__ x, int64_t n, int d, const g8::QuantPar
             const int ppr = outside ? NGC * 4 : 32;
             const int n_items = ROWS * ppr / LOAD_THREADS;              // 8 or 12 per thread and stage
             const int step_rr = LOAD_THREADS / ppr, step_pc = LOAD_THREADS % ppr;
+            // every item's (stage offset, source offset, row) is the same in every stage: computed once, kept in
+            // registers (a first version did this arithmetic per piece and was slower than loading whole rows)
+            constexpr int MAX_ITEMS = ROWS * NGC * 4 / LOAD_THREADS;    // 12
+            int dst_pk[MAX_ITEMS], src_off[MAX_ITEMS];                  // dst_pk = byte offset in the stage | row << 16
+            {
+                int rr = lt / ppr, pc = lt % ppr;
+#pragma unroll
+                for (int it = 0; it < MAX_ITEMS; ++it) {
+                    const int slot = pc >> 2;
+                    const int col = (slot < 8 ? mb * 128 + slot * 16 : js * STRIPE + (slot - 8) * 16) + (pc & 3) * 4;
+                    dst_pk[it] = (rr * raw_stride + ((pc ^ (rr & 7)) << 4)) | (rr << 16);
+                    src_off[it] = rr * d + col;
+                    rr += step_rr; pc += step_pc;
+                    if (pc >= ppr) { pc -= ppr; ++rr; }
+                }
+            }
             for (int st = 0; st < n_stages; ++st) {
                 const int rs = st % RAW_STAGES;
                 mbar_wait(&raw_empty[rs], ((st / RAW_STAGES) & 1) ^ 1);
                 const int64_t row0 = r0 + (int64_t)st * ROWS;
-                const int64_t rows_left = r1 - row0;                    // >= 1
+                const int rows_left = (int)min(r1 - row0, (int64_t)ROWS);   // >= 1
                 unsigned char *stage = sR + rs * raw_bytes;
-                int rr = lt / ppr, pc = lt % ppr;
-                for (int it = 0; it < n_items; ++it) {
-                    const int slot = pc >> 2;
-                    const int col = (slot < 8 ? mb * 128 + slot * 16 : js * STRIPE + (slot - 8) * 16) + (pc & 3) * 4;
-                    const bool in = rr < rows_left;
-                    cp_async_cg16(stage + rr * raw_stride + ((pc ^ (rr & 7)) << 4), in ? x + (row0 + rr) * (int64_t)d + col : x, in ? 16 : 0);
-                    rr += step_rr; pc += step_pc;
-                    if (pc >= ppr) { pc -= ppr; ++rr; }
+                const float *xs = x + row0 * (int64_t)d;
+#pragma unroll
+                for (int it = 0; it < MAX_ITEMS; ++it) {
+                    if (it < n_items) {                                  // (uniform: 8 items when the stripe is inside the block)
+                        const bool in = (dst_pk[it] >> 16) < rows_left;
+                        cp_async_cg16(stage + (dst_pk[it] & 0xFFFF), in ? xs + src_off[it] : x, in ? 16 : 0);
+                    }
                 }
                 cp_async_arrive_noinc(&raw_full[rs]);
             }

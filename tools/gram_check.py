@@ -49,7 +49,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         sym = float(np.max(np.abs(c - c.T)) / np.max(np.abs(c)))
         print(f"[{mode}] n={n} d={d}: {e0.elapsed_time(e1) / 5:.3f} ms, asym {sym:.1e}, trace/n {np.trace(c) / (n - 1):.6f}", flush=True)
 else:
-    for mode in ("i8", "v3"):
+    for mode in os.environ.get("GRAM_CHECK_MODES", "i8,v3").split(","):
         env = dict(os.environ, CLEORA_B200_GRAM=mode)
         try:
             r = subprocess.run([sys.executable, __file__, "child"], env=env, timeout=300, capture_output=True, text=True)
