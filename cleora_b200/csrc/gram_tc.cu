@@ -18,8 +18,10 @@
 // One CTA = a 128 x 64 output tile (row block i, column stripe j at or right of block i -- every G_s is symmetric, the
 // combine kernel mirrors the rest) for a slice of rows: TMEM holds the 7 weight-group accumulators of 128 x 64 int32 =
 // 448 of its 512 columns.  Per 32-row stage: 4 loader warps stage the rows (cp.async, 4 stages deep), 8 converter warps
-// quantise all d columns into four byte planes in a canonical no-swizzle UMMA layout (MN-major for d = 256, K-major
-// for d = 128), one lane issues the 16 tcgen05.mma (both operands are views of the planes: A = the 128 columns of block
+// quantise them into four byte planes in a canonical no-swizzle UMMA layout (MN-major for d >= 256, K-major for d = 128)
+// -- since round 2 only the 128 + 64 columns the tile reads, in a compact staging whose size does not depend on d, which
+// is what admits d = 384 and 512 (template parameter NEEDED; the round-1 form stages all d columns) --, one lane issues
+// the 16 tcgen05.mma (both operands are views of the planes: A = the 128 columns of block
 // i in plane k, B = the stripe's 64 columns in plane l), and 4 drain warps move the accumulators to int64 global memory
 // every 192 stages.
 // Round-2 measurements (profiles/r2d_*): the shared-memory port bounds this kernel, not the tensor pipe (which issues a

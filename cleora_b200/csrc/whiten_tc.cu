@@ -8,9 +8,13 @@
 // Shape: one CTA = 128 rows of x (UMMA M = 128), all N output columns (one UMMA N = N <= 256 accumulator; 256 < N <= 512
 // runs the two column halves of a row tile as two passes into the two TMEM buffers), K = d in chunks of 32.
 // Warp roles (352 threads, persistent over row tiles):
-//   warps 0-3  A producers: thread = row; 128-bit loads of 32 floats, centre, split hi/lo, 16-byte stores into the
-//              canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices, LBO 128 B, SBO 1024 B);
-//   warps 4-7  epilogue: tcgen05.ld of the warp's 32 TMEM lanes (thread = row), optional row L2 norm, then every 32 x 32
+//   warps 0-3  A producers: centre, split hi/lo, 16-byte stores into the A tiles.  Default (ASW = 1, round 2): eight lanes
+//              own the eight 16-byte chunks of one 128-byte row of the stage -- coalesced 128-bit loads, 4 whole lines per
+//              warp instruction -- and the tiles are in the SWIZZLE_128B K-major layout (chunk c of row r at chunk
+//              c ^ (r % 8): conflict-free STS.128).  ASW = 0 (round 1): thread = row, canonical K-major no-swizzle layout
+//              (8-row x 16-byte core matrices, LBO 128 B, SBO 1024 B) -- every warp load touched 32 different lines;
+//   warps 4-7  epilogue: tcgen05.ld of the warp's 32 TMEM lanes (thread = row), optional row L2 norm (one division per
+//              row, a multiplication per element), then every 32 x 32
 //              block goes through a padded shared-memory tile so that rows leave as 128-byte pieces, four rows per
 //              store instruction -- coalesced for HBM and, in the fused-collective modes (PeerOut), for NVLink: the
 //              same rows into the peers' copies (all-gather) or each 32-column slice into its owner's column-sharded
